@@ -1,0 +1,395 @@
+#!/usr/bin/env python3
+"""bench.py -- the measurement contract of this repo.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
+
+Default workload = BASELINE.json configs[1]: Cornell box, the global_illumination example kernel
+(one sample per frame, seed = frameCount), 1920x1080, 64 frames kept as a running mean on the device,
+4 bounces, one B200.  A "step" is one such 64-spp frame.  metric = Mrays/s (every BVH traversal call is
+one ray: primary + shadow + GI extension), ms_per_step = ms/frame 1080p 64spp.
+
+N > 1 (torchrun, one rank per GPU): sample split -- rank r renders frames r, r+N, ... of a 64*N-spp
+frame into its own FP32 accumulator with weight 1/(64N); one NCCL all-reduce(sum) per step combines
+them (weak scaling: per-GPU work is fixed).  Time = CUDA events on the stream the kernels run on, max
+over ranks.
+
+--impl reference: the reference has no CPU implementation of this path and its OpenCL kernels cannot
+run here (no OpenCL ICD), so this arm times the CPU restatement of the same kernel (oracle/, "port")
+on all host cores, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from lens_trace_b200 import layouts as L  # noqa: E402
+
+WORKLOADS = {
+    # name: (model, kernel, width, height, frames, max_ray_depth, description)
+    "cornell_gi_1080p_64spp": ("cornell_box", L.KERNEL_GI, 1920, 1080, 64, 4,
+                               "Cornell box, global_illumination example kernel, 1080p, 64 spp running mean, 4 bounces"),
+    "cornell_primary_512": ("cornell_box", L.KERNEL_BASIC_CL, 512, 512, 1, 0,
+                            "Cornell box, basic kernel, 512x512 primary rays 1 spp"),
+    "cornell_custom_1080p_16": ("cornell_box", L.KERNEL_CUSTOM_BARY, 1920, 1080, 16, 0,
+                                "custom_kernel (barycentric) on the Cornell OBJ, 1080p, 16 accumulated frames"),
+    "synth1m_shadow_1080p": ("synth:707", L.KERNEL_ACCUMULATOR, 1920, 1080, 1, 0,
+                             "synthetic 1M-triangle mesh, primary + shadow rays, 1080p 1 spp"),
+    "synth1m_gi_1080p_16spp": ("synth:707", L.KERNEL_GI, 1920, 1080, 16, 4,
+                               "synthetic 1M-triangle mesh, GI 4 bounces, 1080p 16 spp"),
+    "synth5m_gi_4k_256spp": ("synth:1581", L.KERNEL_GI, 3840, 2160, 256, 4,
+                             "synthetic 5M-triangle mesh, GI 4 bounces, 4K 256 spp"),
+}
+DEFAULT_WORKLOAD = "cornell_gi_1080p_64spp"
+
+
+def load_scene(model):
+    from lens_trace_b200 import host
+    if model.startswith("synth:"):
+        n = int(model.split(":")[1])
+        path = "/tmp/lt_synth_%d_%d.obj" % (n, os.getpid())
+        host.write_synthetic_scene(path, n, 0x5EED)
+        sb = host.load_scene_buffers(path)
+        for p in (path, path[:-4] + ".mtl"):
+            try:
+                os.remove(p)
+            except OSError:
+                pass
+        return sb
+    return host.load_scene_buffers(os.path.join(ROOT, "resources", "models", model + ".obj"))
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d.get("hbm_gbs", 6650.0), "sm_max_mhz": d.get("sm_max_mhz", 1965.0), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0, "source": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 6:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        self.stop_flag = True
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(sm)}
+
+
+def cpu_oracle_rate(sb, kernel, w, h, depth, frame_list, threads=0):
+    """Mrays/s of the CPU restatement on `frame_list` full frames; returns (mrays_s, rays, seconds, cores)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import lt_oracle as O
+    cores = os.cpu_count() or 1
+    rays, t = 0, 0.0
+    for f in frame_list:
+        cam = L.make_camera(0, 2.5, -50, 0.0, f)
+        t0 = time.perf_counter()
+        _, st = O.render(kernel, sb, cam, w, h, max_ray_depth=depth if depth else 16, threads=threads, with_stats=True)
+        t += time.perf_counter() - t0
+        rays += st.rays
+    return rays / t / 1e6, rays, t, (threads if threads > 0 else cores)
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the CPU port of the reference kernel, all host cores, bounded sample per step."""
+    if rank != 0:
+        return
+    model, kernel, w, h, frames, depth, desc = WORKLOADS[args.workload]
+    sb = load_scene(model)
+    per_step = max(1, min(frames, 2))
+    cpu_oracle_rate(sb, kernel, w, h, depth, [0])  # warm-up (page in, build)
+    for i in range(max(0, args.warmup - 1)):
+        cpu_oracle_rate(sb, kernel, w, h, depth, [i])
+    rays, secs, cores = 0, 0.0, 1
+    for s in range(args.steps):
+        _, r, t, cores = cpu_oracle_rate(sb, kernel, w, h, depth, [s * per_step + k for k in range(per_step)])
+        rays += r
+        secs += t
+    value = rays / secs / 1e6
+    sample = "%d of the %d frames per step at full %dx%d (frameCount = step*%d + k)" % (per_step, frames, w, h, per_step)
+    line = {
+        "impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3 * (frames / per_step),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "description": desc, "width": w, "height": h, "frames_per_step": frames,
+                   "max_ray_depth": depth, "note": "ms_per_step extrapolated from the bounded sample to the whole step"},
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def reference_cuda_kernel_rate(sb, w, h):
+    """Kernel-only rate of the reference's own CUDA kernel (NVRTC build of its basic.cu) on this GPU,
+    same buffers, primary rays -- context for the north star's 10x target.  None when oracle/_ref is absent."""
+    import ctypes as C
+    lib_path = os.path.join(ROOT, "oracle", "_ref", "libltref.so")
+    kpath = os.path.join(ROOT, "oracle", "_ref", "resources", "kernels", "cuda", "basic.cu")
+    if not (os.path.exists(lib_path) and os.path.exists(kpath)):
+        return None
+    try:
+        lib = C.CDLL(lib_path)
+        lib.ltref_renderer_cuda_create.restype = C.c_void_p
+        lib.ltref_time_kernel.restype = C.c_double
+        lib.ltref_time_kernel.argtypes = [C.c_char_p, C.c_char_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64,
+                                          C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64,
+                                          C.c_uint64, C.c_uint64, C.c_uint, C.c_uint, C.c_int, C.c_int, C.c_void_p]
+        lib.ltref_renderer_cuda_create()
+        cam = L.make_camera(0, 2.5, -50)
+        res = {}
+        for bx, by in ((32, 1), (8, 8)):
+            ms = lib.ltref_time_kernel(kpath.encode(), b"linearKernel", sb.nodes.ctypes.data, sb.nodes.nbytes,
+                                       sb.prims.ctypes.data, sb.prims.nbytes, sb.materials.ctypes.data,
+                                       sb.materials.nbytes, sb.lights.ctypes.data, sb.lights.nbytes, cam.ctypes.data,
+                                       w, h, 3, bx, by, 3, 10, None)
+            if ms > 0:
+                res["block_%dx%d" % (bx, by)] = {"ms": ms, "mrays_s": w * h / ms / 1e3}
+        return res or None
+    except Exception as e:  # pragma: no cover
+        return {"error": str(e)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-cuda", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from lens_trace_b200 import capi
+
+    if not torch.cuda.is_available():
+        sys.exit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference for the CPU port)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    model, kernel, w, h, frames, depth, desc = WORKLOADS[args.workload]
+    sb = load_scene(model)
+    ctx = capi.Context(local_rank)
+    scene = ctx.upload(sb)
+    upload_ms = ctx.stats().upload_ms
+    # a non-default torch stream: lt_ctx_set_stream(NULL) would mean "the context's own stream", and
+    # torch.cuda.Event only sees the stream it is recorded on
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
+
+    acc = torch.zeros((h, w, 3), dtype=torch.float32, device=dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
+    pinned = torch.empty((h, w, 3), dtype=torch.float32).pin_memory()
+
+    def make_step_params(flags=0):
+        if world == 1:
+            return capi.make_params(kernel, w, h, max_ray_depth=depth, frames=frames,
+                                    accum_mode=L.ACCUM_RUNNING_MEAN, flags=flags)
+        return capi.make_params(kernel, w, h, max_ray_depth=depth, frames=frames, frame_stride=world,
+                                accum_mode=L.ACCUM_WEIGHTED_SUM, accum_weight=1.0 / (frames * world), flags=flags)
+
+    cam = L.make_camera(0, 2.5, -50, 0.0, rank if world > 1 else 0)
+
+    def step():
+        """one frame of the workload: all samples of this rank, then the exchange step"""
+        if world > 1:
+            acc.zero_()
+        ctx.render_device(scene, cam, make_step_params(), acc.data_ptr(), sync=False)
+        if world > 1:
+            dist.all_reduce(acc)
+
+    # counters of one step (untimed): rays and the reference-order node/triangle tests
+    ctx.render_device(scene, cam, make_step_params(L.FLAG_STATS), acc.data_ptr(), sync=True)
+    st = ctx.stats()
+    counts = torch.tensor([st.rays, st.node_tests, st.tri_tests], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(counts)
+    rays, node_tests, tri_tests = [float(x) for x in counts.tolist()]
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    events = []
+    kernel_events = []
+    for _ in range(args.steps):
+        flush.fill_(1.0)  # L2 flush between timed iterations (untimed)
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record(stream)
+        if world > 1:
+            acc.zero_()
+        ctx.render_device(scene, cam, make_step_params(), acc.data_ptr(), sync=False)
+        e1.record(stream)
+        if world > 1:
+            dist.all_reduce(acc)
+        e2.record(stream)
+        events.append((e0, e2))
+        kernel_events.append((e0, e1))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.summary()
+    total_ms = sum(a.elapsed_time(b) for a, b in events)
+    kernel_ms = sum(a.elapsed_time(b) for a, b in kernel_events)
+    t = torch.tensor([total_ms, kernel_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, kernel_ms = t.tolist()
+    ms_per_step = total_ms / args.steps
+    value = rays / (ms_per_step * 1e-3) / 1e6
+
+    # end to end through the public C-ABI with host buffers (lt_render: H2D of the camera, kernels, D2H)
+    e2e_times = []
+    for i in range(max(2, min(args.steps, 3)) + 1):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        if world == 1:
+            ctx.render_into(scene, cam, make_step_params(), pinned.data_ptr())
+        else:
+            acc.zero_()
+            ctx.render_device(scene, cam, make_step_params(), acc.data_ptr(), sync=False)
+            dist.all_reduce(acc)
+            pinned.copy_(acc, non_blocking=False)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if i > 0:
+            e2e_times.append(dt)
+    e2e_t = torch.tensor([sum(e2e_times) / len(e2e_times)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_s = e2e_t.item()
+
+    if rank == 0:
+        pk = peaks()
+        sm_count = st.sm_count or 148
+        fp32_peak = sm_count * 128 * pk["sm_max_mhz"] * 1e6  # lane-instructions / s
+        alg_instr = 12.0 * node_tests + 45.0 * tri_tests
+        alg_bytes = 32.0 * node_tests + 36.0 * tri_tests
+        k_s = kernel_ms / args.steps * 1e-3
+        scene_bytes = sb.nodes.nbytes + sb.prims.nbytes
+        level = "hbm" if scene_bytes > 126e6 else ("l2" if scene_bytes > 200e3 else "l1")
+        l1_peak = sm_count * 128 * pk["sm_max_mhz"] * 1e6 / 1e9  # GB/s, nominal 128 B/clk/SM
+        bw_peak = {"hbm": pk["hbm_gbs"], "l2": None, "l1": l1_peak}[level]
+        fp32 = {"achieved": alg_instr / k_s / 1e12, "peak": fp32_peak / 1e12, "unit": "T lane-instr/s",
+                "frac": alg_instr / k_s / fp32_peak}
+        fetch = {"level": level, "achieved": alg_bytes / k_s / 1e9, "peak": bw_peak, "unit": "GB/s",
+                 "frac": (alg_bytes / k_s / 1e9 / bw_peak) if bw_peak else None,
+                 "peak_source": ("MEASURED_PEAKS.json (%s)" % pk["source"]) if level == "hbm" else
+                 ("nominal 128 B/clk/SM x SMs x sm_max_mhz" if level == "l1" else "L2 bandwidth not measured")}
+        t_fp32 = alg_instr / fp32_peak
+        t_fetch = (alg_bytes / (bw_peak * 1e9)) if bw_peak else 0.0
+        if t_fetch >= t_fp32:
+            roof = {"bound": level, "achieved": fetch["achieved"], "peak": fetch["peak"], "unit": "GB/s",
+                    "frac": fetch["frac"], "traffic": None}
+        else:
+            roof = {"bound": "fp32", "achieved": fp32["achieved"], "peak": fp32["peak"], "unit": "T lane-instr/s",
+                    "frac": fp32["frac"], "traffic": None}
+        roof.update({"kernel": "k_path" if kernel >= 3 else "k_flat", "kernel_ms_per_launch": kernel_ms / args.steps,
+                     "algorithmic_bytes_per_launch": alg_bytes, "algorithmic_fp32_instr_per_launch": alg_instr,
+                     "node_tests_per_ray": node_tests / rays, "tri_tests_per_ray": tri_tests / rays,
+                     "fp32_issue": fp32, "node_fetch": fetch,
+                     "hbm_view": {"achieved": alg_bytes / k_s / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                                  "frac": alg_bytes / k_s / 1e9 / pk["hbm_gbs"], "peak_source": pk["source"]}})
+        line = {
+            "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "description": desc, "width": w, "height": h,
+                       "frames_per_step_per_gpu": frames, "max_ray_depth": depth, "rays_per_step": rays,
+                       "parallelism": "spp-split x%d + 1 all-reduce/step" % world if world > 1 else "single GPU",
+                       "l2": "flushed between timed steps (256 MB write); scene is %d bytes" % scene_bytes,
+                       "scene_upload_ms": upload_ms},
+            "roofline": roof,
+            "e2e": {"value": rays / e2e_s / 1e6, "unit": "Mrays/s", "ms_per_step": e2e_s * 1e3,
+                    "h2d_bytes_per_step": 28, "d2h_bytes_per_step": int(w * h * 3 * 4),
+                    "api": "lt_render (C-ABI, host output buffer)" if world == 1 else
+                    "lt_render_device + NCCL all-reduce + D2H"},
+            "gpu_launches": args.steps * 1,
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            per = max(1, min(frames, 8))
+            v, r, secs, cores = cpu_oracle_rate(sb, kernel, w, h, depth, list(range(per)))
+            line["cpu_baseline"] = {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "port",
+                                    "sample": "frames 0..%d of the %d at full %dx%d (%.1f s of CPU work)" % (
+                                        per - 1, frames, w, h, secs)}
+        if world == 1 and not args.no_ref_cuda:
+            # the reference's CUDA kernel only exists for primary rays (basic.cu); same scene, same size
+            ref = reference_cuda_kernel_rate(sb, w, h)
+            if ref:
+                pp = capi.make_params(L.KERNEL_BASIC_CU, w, h)
+                ctx.set_stream(None)
+                for _ in range(3):
+                    ctx.render_device(scene, L.make_camera(0, 2.5, -50), pp, acc.data_ptr(), sync=True)
+                mine_ms = []
+                for _ in range(10):
+                    ctx.render_device(scene, L.make_camera(0, 2.5, -50), pp, acc.data_ptr(), sync=True)
+                    mine_ms.append(ctx.stats().kernel_ms)
+                mine = sum(mine_ms) / len(mine_ms)
+                line["reference_cuda_backend"] = {
+                    "what": "primary rays (basic.cu), %dx%d, kernel-only, same buffers, same GPU" % (w, h),
+                    "reference_kernel": ref, "this_repo_kernel": {"ms": mine, "mrays_s": w * h / mine / 1e3}}
+        print(json.dumps(line), flush=True)
+
+    scene.release()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,146 @@
+/*
+ * lens_trace_b200.h -- C-ABI of the B200-native ray-scene hot path (liblt_b200.so).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++ or torch types.  The host-side
+ * C++ classes in include/lens_trace/ (RendererCUDA / RendererOpenCL::render) call only these
+ * entry points; a maintainer of the reference would bind the same calls from
+ * src/cuda/renderer_cuda.cpp:41-140.
+ *
+ * Buffers are passed in the reference's own layouts so its AccelerationStructureExplicit, Model
+ * and Camera objects can feed this library unchanged:
+ *   nodes      LinearBVHNode[]  32 B  (include/lens_trace/acceleration_structure_explicit.h:20-32)
+ *   primitives Primitive[]      76 B  (include/lens_trace/acceleration_structure_explicit.h:34-42)
+ *   materials  Material[]       32 B  (include/lens_trace/model.h:26-31)
+ *   lights     LightContainer  260 B  (include/lens_trace/acceleration_structure_explicit.h:44-47)
+ *   camera     7 x 32-bit       28 B  (src/camera.cpp:14-19: pos[3], yaw, pitch, roll, frameCount)
+ *
+ * Error convention: 0 = ok, negative = error; message through lt_last_error().  There is no CPU
+ * fallback: every compute entry point fails with LT_ERR_NO_DEVICE when no CUDA device is usable.
+ */
+#ifndef LENS_TRACE_B200_H
+#define LENS_TRACE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LT_API_VERSION 1
+
+enum lt_status {
+  LT_OK = 0,
+  LT_ERR_INVALID = -1,    /* bad argument / malformed buffer */
+  LT_ERR_NO_DEVICE = -2,  /* no usable CUDA device (no fallback exists) */
+  LT_ERR_CUDA = -3,       /* a CUDA call failed; see lt_last_error */
+  LT_ERR_UNSUPPORTED = -4 /* unknown kernel file / option */
+};
+
+/* One id per kernel source file the reference ships (replaces the run-time compile of
+ * RenderProperties*::kernelFilePath, src/cuda/renderer_cuda.cpp:20-39,52-55 and
+ * src/opencl/renderer_opencl.cpp:22-54). */
+enum lt_kernel {
+  LT_KERNEL_BASIC_CU = 0,    /* resources/kernels/cuda/basic.cu */
+  LT_KERNEL_BASIC_CL = 1,    /* resources/kernels/opencl/basic.cl */
+  LT_KERNEL_CUSTOM_BARY = 2, /* examples/custom_kernel/resources/kernels/custom_opencl.cl */
+  LT_KERNEL_LIGHTING25 = 3,  /* resources/kernels/opencl/basic_lighting.cl */
+  LT_KERNEL_ACCUMULATOR = 4, /* examples/accumulator/resources/kernels/accumulator.cl */
+  LT_KERNEL_GI25 = 5,        /* resources/kernels/opencl/global_illumination.cl */
+  LT_KERNEL_GI = 6,          /* examples/global_illumination/resources/kernels/global_illumination.cl */
+  LT_KERNEL_COUNT = 7
+};
+
+/* How successive frames of one lt_render call are combined. */
+enum lt_accum_mode {
+  LT_ACCUM_NONE = 0,         /* output = the last frame's sample (reference render() semantics) */
+  LT_ACCUM_RUNNING_MEAN = 1, /* examples/accumulator/resources/shaders/accumulator.frag:10-19, FP32 */
+  LT_ACCUM_WEIGHTED_SUM = 2  /* acc += weight * sample  (multi-GPU sample split: all-reduce(sum) gives the mean) */
+};
+
+enum lt_flags {
+  LT_FLAG_STATS = 1 << 0, /* count rays / node tests / triangle tests in the reference's traversal order
+                             (no any-hit early-out); results via lt_last_stats. Not for timed runs. */
+  LT_FLAG_CULL = 1 << 1   /* opt-in: skip subtrees whose entry distance exceeds the current hit (see DESIGN.md;
+                             identical output is validated, not guaranteed) */
+};
+
+typedef struct lt_ctx lt_ctx;
+typedef struct lt_scene lt_scene;
+
+typedef struct lt_render_params {
+  uint32_t struct_size;   /* = sizeof(lt_render_params) */
+  int32_t kernel;         /* enum lt_kernel */
+  int32_t kernel_mode;    /* 0 = linearKernel, 1 = tileKernel (KernelMode, include/lens_trace/structures.h:20-23) */
+  int32_t width;          /* imageDimensions[0] */
+  int32_t height;         /* imageDimensions[1] */
+  int32_t depth;          /* imageDimensions[2]; floats per pixel, 3 are written (basic.cu:344,361-363) */
+  int32_t max_ray_depth;  /* GI bounce cap; 0 = the reference constant 16 (global_illumination.cl:308) */
+  int32_t frames;         /* >= 1: frames rendered by this call; frame k uses frameCount = camera.frameCount + k*frame_stride */
+  uint32_t frame_stride;  /* 0 is treated as 1 */
+  int32_t accum_mode;     /* enum lt_accum_mode */
+  float accum_weight;     /* LT_ACCUM_WEIGHTED_SUM only */
+  int32_t flags;          /* enum lt_flags */
+  int32_t block_x;        /* thread-block shape hint (ThreadOrganizationCUDA.blockSize); 0 = library default. */
+  int32_t block_y;        /* Output never depends on it (tests/cuda_renderer_test.cc:51-115). */
+} lt_render_params;
+
+typedef struct lt_stats {
+  uint64_t rays;        /* traversal calls (primary + shadow + extension + lens segments) */
+  uint64_t node_tests;  /* boxes tested, reference traversal order */
+  uint64_t tri_tests;   /* triangle tests executed, reference traversal order */
+  float kernel_ms;      /* device time of the render kernels of the last lt_render* call (CUDA events) */
+  float upload_ms;      /* device time of the last lt_scene_upload (H2D + re-flatten) */
+  int32_t kernel_launches; /* kernels launched by the last lt_render* call */
+  int32_t sm_count;
+} lt_stats;
+
+/* --- context: replaces RendererCUDA::RendererCUDA() (src/cuda/renderer_cuda.cpp:10-14). --- */
+int lt_ctx_create(int device_ordinal, lt_ctx** out_ctx);
+void lt_ctx_destroy(lt_ctx* ctx);
+/* Last error message of ctx (or of the failed lt_ctx_create when ctx == NULL). Never NULL. */
+const char* lt_last_error(const lt_ctx* ctx);
+/* Render on this CUDA stream (cudaStream_t as void*); NULL = the context's own stream. */
+int lt_ctx_set_stream(lt_ctx* ctx, void* cuda_stream);
+
+/* --- scene: replaces the per-call cuMemAlloc + cuMemcpyHtoD of nodes, primitives, materials and
+ * the light container (src/cuda/renderer_cuda.cpp:90-104).  Uploads once and re-flattens on the
+ * device into the 64-byte child-pair node / 48-byte triangle layout. --- */
+int lt_scene_upload(lt_ctx* ctx, const void* nodes, uint64_t node_bytes, const void* primitives,
+                    uint64_t primitive_bytes, const void* materials, uint64_t material_bytes,
+                    const void* light_container, uint64_t light_bytes, lt_scene** out_scene);
+void lt_scene_release(lt_ctx* ctx, lt_scene* scene);
+
+/* --- render: replaces cuLaunchKernel + cuCtxSynchronize + cuMemcpyDtoH
+ * (src/cuda/renderer_cuda.cpp:113-139).  Synchronous.  host_out (may be NULL) receives
+ * width*height*depth floats: the sample (LT_ACCUM_NONE) or the accumulator. --- */
+int lt_render(lt_ctx* ctx, lt_scene* scene, const void* camera28, const lt_render_params* params,
+              float* host_out);
+/* Same, but the result stays in device memory (device_out: width*height*depth floats on ctx's
+ * device, e.g. a torch tensor's data_ptr; used as the accumulator when accum_mode != NONE).
+ * Asynchronous on the context stream unless sync != 0. */
+int lt_render_device(lt_ctx* ctx, lt_scene* scene, const void* camera28, const lt_render_params* params,
+                     float* device_out, int sync);
+
+/* The context-owned accumulator used by lt_render (reset = next running-mean frame restarts). */
+int lt_accum_reset(lt_ctx* ctx);
+int lt_accum_read(lt_ctx* ctx, float* host_out, uint64_t float_count);
+
+/* Hit record of the primary ray of every pixel (the payload of basic.cu:57-63 after intersect()):
+ * ids = primitiveIndex, hit = hitType, tuv = t,u,v.  Any pointer may be NULL.  Host pointers. */
+int lt_primary_hits(lt_ctx* ctx, lt_scene* scene, const void* camera28, int kernel, int width, int height,
+                    int32_t* ids, int32_t* hit, float* tuv);
+
+int lt_last_stats(const lt_ctx* ctx, lt_stats* out_stats);
+
+/* Maps RenderProperties*::kernelFilePath to an lt_kernel by the file's base name and, when the file
+ * is readable, its defining text (SAMPLE_COUNT, epsilon); returns LT_ERR_UNSUPPORTED for a file that
+ * is not one of the shipped kernels. */
+int lt_kernel_from_path(const char* kernel_file_path);
+const char* lt_kernel_name(int kernel);
+
+int lt_api_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

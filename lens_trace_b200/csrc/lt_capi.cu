@@ -1,0 +1,420 @@
+// lt_capi.cu -- the C-ABI of liblt_b200.so (include/lens_trace_b200.h): context, scene upload with
+// device-side re-flatten, render entry points.  No CPU fallback: every compute call needs a CUDA
+// device and fails with LT_ERR_NO_DEVICE / LT_ERR_CUDA otherwise.
+#include "lens_trace_b200.h"
+#include "lt_internal.h"
+
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+struct lt_ctx {
+  int device = 0;
+  cudaStream_t ownStream = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string error;
+  float* dOut = nullptr;  // context-owned output / accumulator
+  size_t outFloats = 0;
+  LtCounters* dCounters = nullptr;
+  lt_stats stats = {};
+};
+
+struct lt_scene {
+  RefNode* dNodes = nullptr;
+  RefPrim* dPrims = nullptr;
+  RefMaterial* dMats = nullptr;
+  RefLights* dLights = nullptr;
+  LtWideNode* dWide = nullptr;
+  LtTri* dTris = nullptr;
+  LtSceneDev dev = {};
+};
+
+static thread_local std::string g_error = "";
+
+static int fail(lt_ctx* ctx, int code, const std::string& msg) {
+  if (ctx) ctx->error = msg;
+  g_error = msg;
+  return code;
+}
+
+#define CK(call)                                                                                     \
+  do {                                                                                               \
+    cudaError_t e_ = (call);                                                                         \
+    if (e_ != cudaSuccess)                                                                           \
+      return fail(ctx, LT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));             \
+  } while (0)
+
+extern "C" int lt_api_version(void) { return LT_API_VERSION; }
+
+extern "C" const char* lt_last_error(const lt_ctx* ctx) { return ctx ? ctx->error.c_str() : g_error.c_str(); }
+
+extern "C" int lt_ctx_create(int device_ordinal, lt_ctx** out_ctx) {
+  lt_ctx* ctx = nullptr;
+  if (!out_ctx) return fail(nullptr, LT_ERR_INVALID, "lt_ctx_create: out_ctx is NULL");
+  *out_ctx = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    return fail(nullptr, LT_ERR_NO_DEVICE,
+                std::string("lt_ctx_create: no CUDA device (") + cudaGetErrorString(e) +
+                    "); liblt_b200 has no CPU fallback");
+  }
+  if (device_ordinal < 0 || device_ordinal >= n)
+    return fail(nullptr, LT_ERR_INVALID, "lt_ctx_create: device ordinal out of range");
+  CK(cudaSetDevice(device_ordinal));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device_ordinal));
+  if (prop.major < 10)
+    return fail(nullptr, LT_ERR_NO_DEVICE, "lt_ctx_create: device is not sm_100 (kernels are built for sm_100a only)");
+  ctx = new lt_ctx();
+  ctx->device = device_ordinal;
+  ctx->stats.sm_count = prop.multiProcessorCount;
+  cudaError_t e2 = cudaStreamCreateWithFlags(&ctx->ownStream, cudaStreamNonBlocking);
+  if (e2 == cudaSuccess) e2 = cudaEventCreate(&ctx->ev0);
+  if (e2 == cudaSuccess) e2 = cudaEventCreate(&ctx->ev1);
+  if (e2 == cudaSuccess) e2 = cudaMalloc(&ctx->dCounters, sizeof(LtCounters));
+  if (e2 != cudaSuccess) {
+    std::string m = std::string("lt_ctx_create: ") + cudaGetErrorString(e2);
+    delete ctx;
+    return fail(nullptr, LT_ERR_CUDA, m);
+  }
+  ctx->stream = ctx->ownStream;
+  *out_ctx = ctx;
+  return LT_OK;
+}
+
+extern "C" void lt_ctx_destroy(lt_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->dOut) cudaFree(ctx->dOut);
+  if (ctx->dCounters) cudaFree(ctx->dCounters);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->ownStream) cudaStreamDestroy(ctx->ownStream);
+  delete ctx;
+}
+
+extern "C" int lt_ctx_set_stream(lt_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return fail(nullptr, LT_ERR_INVALID, "lt_ctx_set_stream: ctx is NULL");
+  ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->ownStream;
+  return LT_OK;
+}
+
+// Host-side validation of the reference node array (bounds of every index the kernels will
+// follow) and the depth the traversal stack needs.
+static int validate_tree(const RefNode* nodes, int nodeCount, int primCount, int* stackDepth, std::string* why) {
+  std::vector<std::pair<int, int>> todo;  // (node, number of inner ancestors)
+  todo.reserve(128);
+  todo.push_back({0, 0});
+  long long visited = 0;
+  int maxInner = 0;
+  while (!todo.empty()) {
+    std::pair<int, int> cur = todo.back();
+    todo.pop_back();
+    int i = cur.first, d = cur.second;
+    if (++visited > nodeCount) { *why = "node array is not a tree (cycle or shared child)"; return -1; }
+    const RefNode& n = nodes[i];
+    if (n.primitiveCount > 0) {
+      if (n.offset < 0 || n.offset >= primCount) { *why = "leaf primitivesOffset out of range"; return -1; }
+    } else {
+      if (i + 1 >= nodeCount || n.offset <= i + 1 || n.offset >= nodeCount) {
+        *why = "inner node child index out of range";
+        return -1;
+      }
+      if (n.axis > 2) { *why = "inner node axis > 2"; return -1; }
+      if (d + 1 > maxInner) maxInner = d + 1;
+      todo.push_back({n.offset, d + 1});
+      todo.push_back({i + 1, d + 1});
+    }
+  }
+  *stackDepth = maxInner;
+  return 0;
+}
+
+extern "C" void lt_scene_release(lt_ctx* ctx, lt_scene* s) {
+  if (!s) return;
+  if (ctx) {
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+  }
+  cudaFree(s->dNodes);
+  cudaFree(s->dPrims);
+  cudaFree(s->dMats);
+  cudaFree(s->dLights);
+  cudaFree(s->dWide);
+  cudaFree(s->dTris);
+  delete s;
+}
+
+extern "C" int lt_scene_upload(lt_ctx* ctx, const void* nodes, uint64_t node_bytes, const void* primitives,
+                               uint64_t primitive_bytes, const void* materials, uint64_t material_bytes,
+                               const void* light_container, uint64_t light_bytes, lt_scene** out_scene) {
+  if (!ctx) return fail(nullptr, LT_ERR_INVALID, "lt_scene_upload: ctx is NULL");
+  if (!out_scene) return fail(ctx, LT_ERR_INVALID, "lt_scene_upload: out_scene is NULL");
+  *out_scene = nullptr;
+  if (!nodes || !primitives || !materials || !light_container)
+    return fail(ctx, LT_ERR_INVALID, "lt_scene_upload: NULL buffer");
+  if (node_bytes == 0 || node_bytes % sizeof(RefNode) || primitive_bytes == 0 ||
+      primitive_bytes % sizeof(RefPrim) || material_bytes % sizeof(RefMaterial) ||
+      light_bytes != sizeof(RefLights))
+    return fail(ctx, LT_ERR_INVALID, "lt_scene_upload: buffer size is not a multiple of the reference record size");
+  uint64_t nNodes = node_bytes / sizeof(RefNode), nPrims = primitive_bytes / sizeof(RefPrim);
+  uint64_t nMats = material_bytes / sizeof(RefMaterial);
+  if (nNodes > 0x7fffffffull || nPrims > 0x7ffffffeull)
+    return fail(ctx, LT_ERR_INVALID, "lt_scene_upload: too many nodes/primitives for 32-bit indices");
+  const RefNode* hNodes = (const RefNode*)nodes;
+  const RefPrim* hPrims = (const RefPrim*)primitives;
+  const RefLights* hLights = (const RefLights*)light_container;
+  int stackDepth = 0;
+  std::string why;
+  if (validate_tree(hNodes, (int)nNodes, (int)nPrims, &stackDepth, &why) != 0)
+    return fail(ctx, LT_ERR_INVALID, "lt_scene_upload: " + why);
+  if (stackDepth > 64)
+    return fail(ctx, LT_ERR_INVALID, "lt_scene_upload: tree deeper than 64 (the reference's stack, basic.cu:162)");
+  for (uint64_t i = 0; i < nPrims; i++)
+    if (hPrims[i].materialIndex < 0 || (uint64_t)hPrims[i].materialIndex >= nMats)
+      return fail(ctx, LT_ERR_INVALID, "lt_scene_upload: primitive materialIndex out of range");
+  if (hLights->count > 64) return fail(ctx, LT_ERR_INVALID, "lt_scene_upload: light count > 64");
+  for (uint32_t i = 0; i < 64; i++)
+    if (hLights->primitives[i] >= nPrims)
+      return fail(ctx, LT_ERR_INVALID, "lt_scene_upload: light primitive index out of range");
+
+  CK(cudaSetDevice(ctx->device));
+  lt_scene* s = new lt_scene();
+  int* dFlags = nullptr;
+  int* dRank = nullptr;
+  void* dTemp = nullptr;
+  int nInner = 0;
+  for (uint64_t i = 0; i < nNodes; i++) nInner += hNodes[i].primitiveCount == 0;
+  size_t tempBytes = lt_scan_temp_bytes((int)nNodes);
+  cudaError_t e = cudaSuccess;
+  auto A = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+  A(cudaMalloc(&s->dNodes, node_bytes));
+  A(cudaMalloc(&s->dPrims, primitive_bytes));
+  A(cudaMalloc(&s->dMats, material_bytes ? material_bytes : sizeof(RefMaterial)));
+  A(cudaMalloc(&s->dLights, sizeof(RefLights)));
+  A(cudaMalloc(&s->dWide, sizeof(LtWideNode) * (size_t)(nInner > 0 ? nInner : 1)));
+  A(cudaMalloc(&s->dTris, sizeof(LtTri) * nPrims));
+  A(cudaMalloc(&dFlags, sizeof(int) * nNodes));
+  A(cudaMalloc(&dRank, sizeof(int) * nNodes));
+  A(cudaMalloc(&dTemp, tempBytes ? tempBytes : 16));
+  cudaStream_t st = ctx->stream;
+  A(cudaEventRecord(ctx->ev0, st));
+  A(cudaMemcpyAsync(s->dNodes, nodes, node_bytes, cudaMemcpyHostToDevice, st));
+  A(cudaMemcpyAsync(s->dPrims, primitives, primitive_bytes, cudaMemcpyHostToDevice, st));
+  if (material_bytes) A(cudaMemcpyAsync(s->dMats, materials, material_bytes, cudaMemcpyHostToDevice, st));
+  A(cudaMemcpyAsync(s->dLights, light_container, sizeof(RefLights), cudaMemcpyHostToDevice, st));
+  if (e == cudaSuccess) {
+    lt_launch_inner_flags(s->dNodes, (int)nNodes, dFlags, st);
+    lt_launch_exclusive_scan(dTemp, tempBytes, dFlags, dRank, (int)nNodes, st);
+    lt_launch_reflatten(s->dNodes, (int)nNodes, s->dPrims, (int)nPrims, dRank, s->dWide, s->dTris, st);
+    A(cudaGetLastError());
+  }
+  A(cudaEventRecord(ctx->ev1, st));
+  A(cudaStreamSynchronize(st));
+  cudaFree(dFlags);
+  cudaFree(dRank);
+  cudaFree(dTemp);
+  if (e != cudaSuccess) {
+    lt_scene_release(ctx, s);
+    return fail(ctx, LT_ERR_CUDA, std::string("lt_scene_upload: ") + cudaGetErrorString(e));
+  }
+  cudaEventElapsedTime(&ctx->stats.upload_ms, ctx->ev0, ctx->ev1);
+
+  LtSceneDev& d = s->dev;
+  d.wnodes = s->dWide;
+  d.tris = s->dTris;
+  d.prims = s->dPrims;
+  d.mats = s->dMats;
+  d.lights = s->dLights;
+  for (int k = 0; k < 3; k++) {
+    d.rootMin[k] = hNodes[0].boundsMin[k];
+    d.rootMax[k] = hNodes[0].boundsMax[k];
+  }
+  d.rootRef = hNodes[0].primitiveCount > 0 ? ~hNodes[0].offset : 0;  // inner root is wide node 0
+  d.rootCount = hNodes[0].primitiveCount;
+  d.stackDepth = stackDepth;
+  d.nodeCount = (int)nNodes;
+  d.primCount = (int)nPrims;
+  d.matCount = (int)nMats;
+  *out_scene = s;
+  return LT_OK;
+}
+
+static int check_params(lt_ctx* ctx, const lt_scene* scene, const void* camera28, const lt_render_params* p,
+                        LtLaunch* L) {
+  if (!ctx) return fail(nullptr, LT_ERR_INVALID, "lt_render: ctx is NULL");
+  if (!scene || !camera28 || !p) return fail(ctx, LT_ERR_INVALID, "lt_render: NULL argument");
+  if (p->struct_size != sizeof(lt_render_params))
+    return fail(ctx, LT_ERR_INVALID, "lt_render: params.struct_size mismatch");
+  if (p->kernel < 0 || p->kernel >= LT_KERNEL_COUNT) return fail(ctx, LT_ERR_UNSUPPORTED, "lt_render: unknown kernel id");
+  if (p->width <= 0 || p->height <= 0 || p->depth < 3)
+    return fail(ctx, LT_ERR_INVALID, "lt_render: width/height must be > 0 and depth >= 3");
+  if ((long long)p->width * p->height * p->depth > (1ll << 40)) return fail(ctx, LT_ERR_INVALID, "lt_render: image too large");
+  if (p->frames < 1) return fail(ctx, LT_ERR_INVALID, "lt_render: frames must be >= 1");
+  if (p->accum_mode < 0 || p->accum_mode > 2) return fail(ctx, LT_ERR_INVALID, "lt_render: bad accum_mode");
+  if (p->max_ray_depth < 0) return fail(ctx, LT_ERR_INVALID, "lt_render: max_ray_depth < 0");
+  L->kernel = p->kernel;
+  L->kernelMode = p->kernel_mode ? 1 : 0;
+  L->width = p->width;
+  L->height = p->height;
+  L->depth = p->depth;
+  L->maxRayDepth = p->max_ray_depth;
+  L->frames = p->frames;
+  L->frameStride = p->frame_stride ? p->frame_stride : 1u;
+  L->accumMode = p->accum_mode;
+  L->accumWeight = p->accum_weight;
+  L->flags = p->flags;
+  memcpy(&L->cam, camera28, sizeof(RefCamera));
+  return LT_OK;
+}
+
+static int ensure_out(lt_ctx* ctx, size_t floats) {
+  if (ctx->outFloats >= floats) return LT_OK;
+  if (ctx->dOut) cudaFree(ctx->dOut);
+  ctx->dOut = nullptr;
+  ctx->outFloats = 0;
+  CK(cudaMalloc(&ctx->dOut, floats * sizeof(float)));
+  CK(cudaMemsetAsync(ctx->dOut, 0, floats * sizeof(float), ctx->stream));
+  ctx->outFloats = floats;
+  return LT_OK;
+}
+
+static int render_common(lt_ctx* ctx, lt_scene* scene, const LtLaunch& L, float* dOut, bool sync) {
+  CK(cudaSetDevice(ctx->device));
+  bool stats = (L.flags & LT_FLAG_STATS) != 0;
+  if (stats) CK(cudaMemsetAsync(ctx->dCounters, 0, sizeof(LtCounters), ctx->stream));
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  int launches = lt_launch_render(scene->dev, L, dOut, ctx->dCounters, ctx->stream);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  ctx->stats.kernel_launches = launches;
+  if (sync || stats) {
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaEventElapsedTime(&ctx->stats.kernel_ms, ctx->ev0, ctx->ev1));
+  }
+  if (stats) {
+    LtCounters h;
+    CK(cudaMemcpy(&h, ctx->dCounters, sizeof(h), cudaMemcpyDeviceToHost));
+    ctx->stats.rays = h.rays;
+    ctx->stats.node_tests = h.nodeTests;
+    ctx->stats.tri_tests = h.triTests;
+  }
+  return LT_OK;
+}
+
+extern "C" int lt_render_device(lt_ctx* ctx, lt_scene* scene, const void* camera28, const lt_render_params* params,
+                                float* device_out, int sync) {
+  LtLaunch L;
+  int rc = check_params(ctx, scene, camera28, params, &L);
+  if (rc != LT_OK) return rc;
+  if (!device_out) return fail(ctx, LT_ERR_INVALID, "lt_render_device: device_out is NULL");
+  return render_common(ctx, scene, L, device_out, sync != 0);
+}
+
+extern "C" int lt_render(lt_ctx* ctx, lt_scene* scene, const void* camera28, const lt_render_params* params,
+                         float* host_out) {
+  LtLaunch L;
+  int rc = check_params(ctx, scene, camera28, params, &L);
+  if (rc != LT_OK) return rc;
+  CK(cudaSetDevice(ctx->device));
+  size_t floats = (size_t)L.width * L.height * L.depth;
+  rc = ensure_out(ctx, floats);
+  if (rc != LT_OK) return rc;
+  rc = render_common(ctx, scene, L, ctx->dOut, true);
+  if (rc != LT_OK) return rc;
+  if (host_out) CK(cudaMemcpy(host_out, ctx->dOut, floats * sizeof(float), cudaMemcpyDeviceToHost));
+  return LT_OK;
+}
+
+extern "C" int lt_accum_reset(lt_ctx* ctx) {
+  if (!ctx) return fail(nullptr, LT_ERR_INVALID, "lt_accum_reset: ctx is NULL");
+  CK(cudaSetDevice(ctx->device));
+  if (ctx->dOut) CK(cudaMemsetAsync(ctx->dOut, 0, ctx->outFloats * sizeof(float), ctx->stream));
+  return LT_OK;
+}
+
+extern "C" int lt_accum_read(lt_ctx* ctx, float* host_out, uint64_t float_count) {
+  if (!ctx || !host_out) return fail(ctx, LT_ERR_INVALID, "lt_accum_read: NULL argument");
+  if (!ctx->dOut || float_count > ctx->outFloats) return fail(ctx, LT_ERR_INVALID, "lt_accum_read: no accumulator of that size");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaMemcpy(host_out, ctx->dOut, float_count * sizeof(float), cudaMemcpyDeviceToHost));
+  return LT_OK;
+}
+
+extern "C" int lt_primary_hits(lt_ctx* ctx, lt_scene* scene, const void* camera28, int kernel, int width, int height,
+                               int32_t* ids, int32_t* hit, float* tuv) {
+  if (!ctx) return fail(nullptr, LT_ERR_INVALID, "lt_primary_hits: ctx is NULL");
+  if (!scene || !camera28 || width <= 0 || height <= 0 || kernel < 0 || kernel >= LT_KERNEL_COUNT)
+    return fail(ctx, LT_ERR_INVALID, "lt_primary_hits: bad argument");
+  CK(cudaSetDevice(ctx->device));
+  size_t n = (size_t)width * height;
+  int *dIds = nullptr, *dHit = nullptr;
+  float* dTuv = nullptr;
+  CK(cudaMalloc(&dIds, n * sizeof(int)));
+  CK(cudaMalloc(&dHit, n * sizeof(int)));
+  CK(cudaMalloc(&dTuv, 3 * n * sizeof(float)));
+  RefCamera cam;
+  memcpy(&cam, camera28, sizeof(cam));
+  lt_launch_primary_hits(scene->dev, cam, kernel, width, height, dIds, dHit, dTuv, ctx->stream);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e == cudaSuccess && ids) e = cudaMemcpy(ids, dIds, n * sizeof(int), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && hit) e = cudaMemcpy(hit, dHit, n * sizeof(int), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && tuv) e = cudaMemcpy(tuv, dTuv, 3 * n * sizeof(float), cudaMemcpyDeviceToHost);
+  cudaFree(dIds);
+  cudaFree(dHit);
+  cudaFree(dTuv);
+  if (e != cudaSuccess) return fail(ctx, LT_ERR_CUDA, std::string("lt_primary_hits: ") + cudaGetErrorString(e));
+  return LT_OK;
+}
+
+extern "C" int lt_last_stats(const lt_ctx* ctx, lt_stats* out_stats) {
+  if (!ctx || !out_stats) return LT_ERR_INVALID;
+  *out_stats = ctx->stats;
+  return LT_OK;
+}
+
+static const char* kKernelNames[LT_KERNEL_COUNT] = {"basic.cu",       "basic.cl",          "custom_opencl.cl",
+                                                    "basic_lighting.cl", "accumulator.cl", "global_illumination.cl(25)",
+                                                    "global_illumination.cl(1)"};
+
+extern "C" const char* lt_kernel_name(int kernel) {
+  return (kernel >= 0 && kernel < LT_KERNEL_COUNT) ? kKernelNames[kernel] : "unknown";
+}
+
+extern "C" int lt_kernel_from_path(const char* path) {
+  if (!path) return LT_ERR_INVALID;
+  std::string p(path);
+  size_t slash = p.find_last_of('/');
+  std::string base = slash == std::string::npos ? p : p.substr(slash + 1);
+  if (base == "basic.cu") return LT_KERNEL_BASIC_CU;
+  if (base == "basic.cl") return LT_KERNEL_BASIC_CL;
+  if (base == "custom_opencl.cl") return LT_KERNEL_CUSTOM_BARY;
+  if (base == "basic_lighting.cl") return LT_KERNEL_LIGHTING25;
+  if (base == "accumulator.cl") return LT_KERNEL_ACCUMULATOR;
+  if (base == "global_illumination.cl") {
+    // the resources/ variant blends SAMPLE_COUNT samples per launch (global_illumination.cl:3,408-415),
+    // the example's variant takes one (examples/global_illumination/.../global_illumination.cl:407)
+    FILE* f = fopen(path, "rb");
+    if (f) {
+      std::string text;
+      char buf[4096];
+      size_t n;
+      while ((n = fread(buf, 1, sizeof buf, f)) > 0) text.append(buf, n);
+      fclose(f);
+      if (text.find("lt-pipeline: gi25") != std::string::npos) return LT_KERNEL_GI25;
+      if (text.find("lt-pipeline: gi") != std::string::npos) return LT_KERNEL_GI;
+      return text.find("SAMPLE_COUNT") != std::string::npos ? LT_KERNEL_GI25 : LT_KERNEL_GI;
+    }
+    return p.find("opencl/") != std::string::npos ? LT_KERNEL_GI25 : LT_KERNEL_GI;
+  }
+  g_error = "lt_kernel_from_path: '" + p + "' is not one of the shipped kernels";
+  return LT_ERR_UNSUPPORTED;
+}

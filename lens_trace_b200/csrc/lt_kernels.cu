@@ -1,0 +1,770 @@
+// lt_kernels.cu -- hand-written sm_100a kernels for lens_trace's ray-scene hot path.
+//
+// Path (reference file:line):  camera ray basic.cu:350-358 -> intersect basic.cu:156-243 ->
+// intersectBounds basic.cu:136-154 -> intersectTriangle basic.cu:93-134 -> shade (basic.cu:300-329,
+// basic_lighting.cl:220-277, global_illumination.cl:242-376, custom_opencl.cl:226-244) -> blend /
+// running mean (global_illumination.cl:408-419, accumulator.frag:10-19).
+//
+// Design (DESIGN.md has the long form):
+//  * 64-byte child-pair nodes (LtWideNode) and 48-byte triangles (LtTri), 128-bit loads only.
+//  * One traversal routine shared by primary, shadow and extension rays.  Each thread owns one
+//    pixel and runs a per-thread state machine whose every iteration traces exactly one ray, so a
+//    warp stays converged in the traversal loop while its lanes are at different path stages.
+//  * Traversal stack in shared memory, laid out [level][thread] (bank-conflict free).
+//  * All FP32 arithmetic is written with explicit round-to-nearest intrinsics in the operation
+//    order the reference compiles to, so results do not depend on compiler contraction.
+//  * Tensor cores are not used: nothing here is a dense contraction.
+#include "lt_internal.h"
+
+#include <cub/device/device_scan.cuh>
+#include <float.h>
+#include <math.h>
+
+#define LT_BLOCK 128
+
+// ------------------------------------------------------------------------------------------------
+// exact-arithmetic helpers: never contracted, independent of -fmad
+// ------------------------------------------------------------------------------------------------
+#define FADD(a, b) __fadd_rn((a), (b))
+#define FSUB(a, b) __fsub_rn((a), (b))
+#define FMUL(a, b) __fmul_rn((a), (b))
+#define FFMA(a, b, c) __fmaf_rn((a), (b), (c))
+#define FRCP(a) __frcp_rn((a))
+#define FDIV(a, b) __fdiv_rn((a), (b))
+#define FSQRT(a) __fsqrt_rn((a))
+
+struct Ray {
+  float ox, oy, oz;
+  float dx, dy, dz;
+};
+
+struct Hit {
+  float t, u, v;
+  int prim;  // primitiveIndex (0 when nothing was hit, as in the reference payload)
+  int hit;   // hitType
+};
+
+// dot as basic.cu:71 compiles: fma(z,z', fma(x,x', y*y')) + 0.0f
+__device__ __forceinline__ float dot3z(float ax, float ay, float az, float bx, float by, float bz) {
+  return FADD(FFMA(az, bz, FFMA(ax, bx, FMUL(ay, by))), 0.0f);
+}
+
+// intersectBounds, basic.cu:136-154: lo/hi are the dirIsNeg-selected bounds per axis.
+__device__ __forceinline__ bool slab(float lox, float hix, float loy, float hiy, float loz, float hiz,
+                                     const Ray& r, float ix, float iy, float iz) {
+  float tx0 = FMUL(FSUB(lox, r.ox), ix);
+  float tx1 = FMUL(FSUB(hix, r.ox), ix);
+  float ty0 = FMUL(FSUB(loy, r.oy), iy);
+  float ty1 = FMUL(FSUB(hiy, r.oy), iy);
+  float tz0 = FMUL(FSUB(loz, r.oz), iz);
+  float tz1 = FMUL(FSUB(hiz, r.oz), iz);
+  bool miss1 = (tx0 > ty1) || (ty0 > tx1);
+  float a = (ty0 > tx0) ? ty0 : tx0;
+  float b = (ty1 < tx1) ? ty1 : tx1;
+  bool miss2 = (a > tz1) || (tz0 > b);
+  float b2 = (tz1 < b) ? tz1 : b;
+  return !miss1 && !miss2 && (b2 > 0.0f);
+}
+
+// intersectTriangle, basic.cu:93-134, on the pre-subtracted record.  Returns true when the hit
+// record was replaced (strict t < best, no t > 0 test -- both as in the reference).
+__device__ __forceinline__ bool tri_test(const LtTri* __restrict__ tris, int prim, const Ray& r, float epsThr,
+                                         Hit& h) {
+  const float4* tp = reinterpret_cast<const float4*>(tris + prim);
+  float4 q0 = __ldg(tp), q1 = __ldg(tp + 1), q2 = __ldg(tp + 2);
+  float ax = q0.x, ay = q0.y, az = q0.z;
+  float e1x = q0.w, e1y = q1.x, e1z = q1.y;
+  float e2x = q1.z, e2y = q1.w, e2z = q2.x;
+  float pvx = FFMA(r.dy, e2z, -FMUL(r.dz, e2y));
+  float pvy = FFMA(r.dz, e2x, -FMUL(r.dx, e2z));
+  float pvz = FFMA(r.dx, e2y, -FMUL(r.dy, e2x));
+  float det = dot3z(e1x, e1y, e1z, pvx, pvy, pvz);
+  if (fabsf(det) < epsThr) return false;
+  float inv = FRCP(det);
+  float tx = FSUB(r.ox, ax), ty = FSUB(r.oy, ay), tz = FSUB(r.oz, az);
+  float u = FMUL(dot3z(tx, ty, tz, pvx, pvy, pvz), inv);
+  if (u < 0.0f || u > 1.0f) return false;
+  float qx = FFMA(ty, e1z, -FMUL(tz, e1y));
+  float qy = FFMA(tz, e1x, -FMUL(tx, e1z));
+  float qz = FFMA(tx, e1y, -FMUL(ty, e1x));
+  float v = FMUL(dot3z(r.dx, r.dy, r.dz, qx, qy, qz), inv);
+  if (v < 0.0f || FADD(u, v) > 1.0f) return false;
+  float t = FMUL(dot3z(e2x, e2y, e2z, qx, qy, qz), inv);
+  if (t < h.t) {
+    h.t = t;
+    h.u = u;
+    h.v = v;
+    return true;
+  }
+  return false;
+}
+
+// intersect / intersectIgnorePrimitiveIndex (basic.cu:156-243) on the child-pair layout.
+// Visits children near-first by the sign of the ray direction on the split axis and defers the far
+// child, so triangles are tested in exactly the reference's order; a child whose box is missed is
+// never pushed.  anyHit = stop at the first accepted triangle: exact for shadow rays because the
+// callers read only hitType (basic_lighting.cl:272, global_illumination.cl:296,352).
+// h must be initialised by the caller ({tInit,0,0,0,0}); ignore < 0 = none.
+template <bool STATS>
+__device__ __forceinline__ void trace(const LtSceneDev& sc, const Ray& r, int ignore, float epsThr, bool anyHit,
+                                      Hit& h, int* __restrict__ stk, LtCounters& cnt) {
+  float ix = FRCP(r.dx), iy = FRCP(r.dy), iz = FRCP(r.dz);
+  bool nx = ix < 0.0f, ny = iy < 0.0f, nz = iz < 0.0f;
+  unsigned negMask = (nx ? 1u : 0u) | (ny ? 2u : 0u) | (nz ? 4u : 0u);
+  if (STATS) {
+    cnt.rays++;
+    cnt.nodeTests++;
+    anyHit = false;
+  }
+  // root box (reference node 0)
+  {
+    float lox = nx ? sc.rootMax[0] : sc.rootMin[0], hix = nx ? sc.rootMin[0] : sc.rootMax[0];
+    float loy = ny ? sc.rootMax[1] : sc.rootMin[1], hiy = ny ? sc.rootMin[1] : sc.rootMax[1];
+    float loz = nz ? sc.rootMax[2] : sc.rootMin[2], hiz = nz ? sc.rootMin[2] : sc.rootMax[2];
+    if (!slab(lox, hix, loy, hiy, loz, hiz, r, ix, iy, iz)) return;
+  }
+  int cur = sc.rootRef;
+  int sp = 0;
+  const int stride = LT_BLOCK;
+  if (STATS && cur < 0 && sc.rootCount > 1 && ~cur != ignore) cnt.triTests += (unsigned)(sc.rootCount - 1);
+  while (true) {
+    while (cur >= 0) {
+      const float4* np = reinterpret_cast<const float4*>(sc.wnodes + cur);
+      float4 bx = __ldg(np), by = __ldg(np + 1), bz = __ldg(np + 2);
+      int4 m = __ldg(reinterpret_cast<const int4*>(np) + 3);
+      bool hl = slab(nx ? bx.y : bx.x, nx ? bx.x : bx.y, ny ? by.y : by.x, ny ? by.x : by.y, nz ? bz.y : bz.x,
+                     nz ? bz.x : bz.y, r, ix, iy, iz);
+      bool hr = slab(nx ? bx.w : bx.z, nx ? bx.z : bx.w, ny ? by.w : by.z, ny ? by.z : by.w, nz ? bz.w : bz.z,
+                     nz ? bz.z : bz.w, r, ix, iy, iz);
+      if (STATS) {
+        cnt.nodeTests += 2;
+        // a leaf with primitiveCount n is tested n times by the reference (always the same triangle)
+        unsigned lc = (unsigned)m.w & 0xffffu, rc = (unsigned)m.w >> 16;
+        if (hl && m.x < 0 && lc > 1 && ~m.x != ignore) cnt.triTests += lc - 1;
+        if (hr && m.y < 0 && rc > 1 && ~m.y != ignore) cnt.triTests += rc - 1;
+      }
+      bool axisNeg = (negMask >> m.z) & 1u;
+      int nearRef = axisNeg ? m.y : m.x, farRef = axisNeg ? m.x : m.y;
+      bool hn = axisNeg ? hr : hl, hf = axisNeg ? hl : hr;
+      if (hn) {
+        cur = nearRef;
+        if (hf) {
+          stk[sp * stride] = farRef;
+          sp++;
+        }
+      } else if (hf) {
+        cur = farRef;
+      } else if (sp > 0) {
+        sp--;
+        cur = stk[sp * stride];
+      } else {
+        cur = LT_DONE;
+      }
+    }
+    while (cur < 0 && cur != LT_DONE) {
+      int prim = ~cur;
+      if (prim != ignore) {
+        if (STATS) cnt.triTests++;
+        if (tri_test(sc.tris, prim, r, epsThr, h)) {
+          h.prim = prim;
+          h.hit = 1;
+          if (anyHit) return;
+        }
+      }
+      if (sp > 0) {
+        sp--;
+        cur = stk[sp * stride];
+      } else {
+        cur = LT_DONE;
+      }
+    }
+    if (cur == LT_DONE) return;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-kernel constants (see oracle/lt_oracle.c: flavour_for_kernel)
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ inline float lt_tinit(int kernel) { return kernel == 0 ? 10000000.0f : FLT_MAX; }
+__host__ __device__ inline float lt_eps(int kernel) {
+  // fabs(det) < eps; the macro-defined epsilons are compared in fp64, i.e. against the next float up
+  switch (kernel) {
+    case 0: case 1: case 2: return 0x1.ad7f2ap-24f;  // (float)1e-7: basic.cu:95, basic.cl:78
+    case 3: return 0x1.ad7f2ap-24f;                   // (float)1e-7 >= 1e-7 (double) already
+    default: return 0x1.a36e30p-14f;                  // smallest float >= 1e-4 (double); (float)1e-4 is below
+  }
+}
+
+// camera ray, basic.cu:350-358; fused forms as NVRTC+ptxas emit them (oracle/notes_fma_order.md)
+__device__ __forceinline__ Ray camera_ray(const RefCamera& cam, int px, int py, int width, int height, float& fx,
+                                          float& fy) {
+  fx = FADD(FDIV((float)px, (float)width), -0.5f);
+  fy = FADD(FDIV((float)py, (float)height), -0.5f);
+  float c = cosf(cam.yaw), s = sinf(cam.yaw);
+  float dx0 = FSUB(0.0f, fx);
+  Ray r;
+  r.ox = FADD(fx, cam.position[0]);
+  r.oy = FADD(fy, cam.position[1]);
+  r.oz = FADD(cam.position[2], 0.0f);
+  r.dx = FFMA(dx0, c, FMUL(s, 5.0f));
+  r.dy = FSUB(0.0f, fy);
+  r.dz = FFMA(c, 5.0f, -FMUL(dx0, s));
+  return r;
+}
+
+__device__ __forceinline__ float bary0(float u, float v) {
+  return (float)__dsub_rn(__dsub_rn(1.0, (double)u), (double)v);
+}
+
+// thread -> pixel: a warp covers an 8x4 pixel tile, a block 16x8 (coherent primary rays).
+__device__ __forceinline__ bool thread_pixel(int width, int height, int& px, int& py) {
+  int tilesX = (width + 15) >> 4;
+  int tile = blockIdx.x;
+  int tyi = tile / tilesX, txi = tile - tyi * tilesX;
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  px = (txi << 4) + ((warp & 1) << 3) + (lane & 7);
+  py = (tyi << 3) + ((warp >> 1) << 2) + (lane >> 3);
+  return px < width && py < height;
+}
+
+// running mean / weighted sum / plain store of one finished frame
+struct FrameSink {
+  float acc[3];
+  __device__ __forceinline__ void begin(const LtLaunch& L, const float* out, long long id) {
+    acc[0] = acc[1] = acc[2] = 0.0f;
+    bool needPrev = (L.accumMode == 2) || (L.accumMode == 1 && L.cam.frameCount > 0);
+    if (needPrev) {
+      acc[0] = out[id + 0];
+      acc[1] = out[id + 1];
+      acc[2] = out[id + 2];
+    }
+  }
+  // accumulator.frag:10-19: color = (sample + prev*frameCount) / (frameCount + 1) when frameCount > 0
+  __device__ __forceinline__ void frame(const LtLaunch& L, unsigned frameCount, const float c[3]) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      if (L.accumMode == 1) {
+        float v = c[k];
+        if (frameCount > 0) v = FDIV(FADD(v, FMUL(acc[k], (float)frameCount)), (float)(frameCount + 1u));
+        acc[k] = v;
+      } else if (L.accumMode == 2) {
+        acc[k] = FADD(acc[k], FMUL(L.accumWeight, c[k]));
+      } else {
+        acc[k] = c[k];
+      }
+    }
+  }
+  __device__ __forceinline__ void end(float* out, long long id) const {
+    out[id + 0] = acc[0];
+    out[id + 1] = acc[1];
+    out[id + 2] = acc[2];
+  }
+};
+
+__device__ __forceinline__ void flush_counters(LtCounters* g, const LtCounters& c) {
+  if (g) {
+    atomicAdd(&g->rays, c.rays);
+    atomicAdd(&g->nodeTests, c.nodeTests);
+    atomicAdd(&g->triTests, c.triTests);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel 1: deterministic pipelines -- basic (flat diffuse + lens refraction) and custom barycentric
+// ------------------------------------------------------------------------------------------------
+// barycentric interpolation as basic.cu:257-265 compiles: fma(v, C, fma(A, w0, u*B))
+__device__ __forceinline__ void lerp_fused(const float* a, const float* b, const float* c, float w0, float u,
+                                           float v, float out[3]) {
+#pragma unroll
+  for (int k = 0; k < 3; k++) out[k] = FFMA(v, c[k], FFMA(a[k], w0, FMUL(u, b[k])));
+}
+
+// traceRayThroughLens + refract, basic.cu:79-86,245-298 (operation order: oracle/notes_fma_order.md)
+template <bool STATS>
+__device__ void lens_path(const LtSceneDev& sc, Ray& ray, Hit& h, float tInit, float epsThr, int* stk,
+                          LtCounters& cnt) {
+  const RefPrim* prim = sc.prims + h.prim;
+  const RefMaterial* mat = sc.mats + prim->materialIndex;
+  float w0 = bary0(h.u, h.v);
+  float pos[3], nrm[3];
+  lerp_fused(prim->a, prim->b, prim->c, w0, h.u, h.v, pos);
+  lerp_fused(prim->na, prim->nb, prim->nc, w0, h.u, h.v, nrm);
+
+  float n = FRCP(mat->ior);
+  float c = dot3z(ray.dx, ray.dy, ray.dz, nrm[0], nrm[1], nrm[2]);
+  float sinT2 = (float)__dmul_rn(__dsub_rn(1.0, (double)FMUL(c, c)), (double)FMUL(n, n));
+  float cosT = (float)__dsqrt_rn(__dsub_rn(1.0, (double)sinT2));
+  float k = FFMA(c, -n, -cosT);
+  Ray r2;
+  r2.ox = pos[0]; r2.oy = pos[1]; r2.oz = pos[2];
+  r2.dx = FFMA(ray.dx, n, FMUL(nrm[0], k));
+  r2.dy = FFMA(ray.dy, n, FMUL(nrm[1], k));
+  r2.dz = FFMA(ray.dz, n, FMUL(nrm[2], k));
+  float r2w = FFMA(n, 0.0f, FMUL(k, 0.0f));
+
+  Hit h2 = {tInit, 0.0f, 0.0f, 0, 0};
+  trace<STATS>(sc, r2, h.prim, epsThr, false, h2, stk, cnt);
+
+  prim = sc.prims + h2.prim;
+  mat = sc.mats + prim->materialIndex;
+  w0 = bary0(h2.u, h2.v);
+  lerp_fused(prim->a, prim->b, prim->c, w0, h2.u, h2.v, pos);
+  lerp_fused(prim->na, prim->nb, prim->nc, w0, h2.u, h2.v, nrm);
+
+  float ior = mat->ior;
+  float c2 = FFMA(0.0f, r2w, FFMA(-r2.dz, nrm[2], FFMA(r2.dx, -nrm[0], -FMUL(r2.dy, nrm[1]))));
+  float sinT2b = (float)__dmul_rn(__dsub_rn(1.0, (double)FMUL(c2, c2)), (double)FMUL(ior, ior));
+  float cosTb = (float)__dsqrt_rn(__dsub_rn(1.0, (double)sinT2b));
+  float k2 = FFMA(c2, -ior, -cosTb);
+
+  ray.ox = pos[0]; ray.oy = pos[1]; ray.oz = pos[2];
+  ray.dx = FFMA(r2.dx, ior, -FMUL(k2, nrm[0]));
+  ray.dy = FFMA(r2.dy, ior, -FMUL(k2, nrm[1]));
+  ray.dz = FFMA(r2.dz, ior, -FMUL(k2, nrm[2]));
+  h.t = tInit; h.u = 0.0f; h.v = 0.0f; h.prim = 0; h.hit = 0;
+  trace<STATS>(sc, ray, h2.prim, epsThr, false, h, stk, cnt);
+}
+
+template <bool STATS>
+__global__ void __launch_bounds__(LT_BLOCK) k_flat(LtSceneDev sc, LtLaunch L, float* __restrict__ out,
+                                                   LtCounters* gcnt) {
+  extern __shared__ int smemStack[];
+  int* stk = smemStack + threadIdx.x;
+  int px, py;
+  if (!thread_pixel(L.width, L.height, px, py)) return;
+  LtCounters cnt = {0, 0, 0};
+  float fx, fy;
+  Ray ray = camera_ray(L.cam, px, py, L.width, L.height, fx, fy);
+  const float tInit = lt_tinit(L.kernel), epsThr = lt_eps(L.kernel);
+  float color[3] = {0.0f, 0.0f, 0.0f};
+  Hit h = {tInit, 0.0f, 0.0f, 0, 0};
+  trace<STATS>(sc, ray, -1, epsThr, false, h, stk, cnt);
+  if (h.hit == 1) {
+    if (L.kernel == 2) {  // custom_opencl.cl:240
+      color[0] = h.u;
+      color[1] = h.v;
+      color[2] = bary0(h.u, h.v);
+    } else {  // basic.cu:312-326
+      const RefMaterial* mat = sc.mats + sc.prims[h.prim].materialIndex;
+      if (mat->dissolve < 1.0f) {
+        lens_path<STATS>(sc, ray, h, tInit, epsThr, stk, cnt);
+        if (h.hit == 1) mat = sc.mats + sc.prims[h.prim].materialIndex;
+      }
+      color[0] = mat->diffuse[0];
+      color[1] = mat->diffuse[1];
+      color[2] = mat->diffuse[2];
+    }
+  }
+  long long id = ((long long)py * L.width + px) * L.depth;
+  FrameSink sink;
+  sink.begin(L, out, id);
+  // the image is the same for every frame (no RNG): apply the frame combiner `frames` times
+  for (int f = 0; f < L.frames; f++) sink.frame(L, L.cam.frameCount + (unsigned)f * L.frameStride, color);
+  sink.end(out, id);
+  if (STATS) {
+    cnt.rays *= (unsigned)L.frames;
+    cnt.nodeTests *= (unsigned)L.frames;
+    cnt.triTests *= (unsigned)L.frames;
+    flush_counters(gcnt, cnt);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel 2: stochastic pipelines -- direct lighting, accumulator, global illumination
+// ------------------------------------------------------------------------------------------------
+// fmod(x, M_PI) bit-exact: q is within one of the true quotient, fma gives the exact remainder
+// (both x and q*pi are multiples of 2^-51 and the result is < 2*pi), then one exact correction.
+__device__ __forceinline__ double fmod_pi(double x) {
+  const double PI = 3.14159265358979323846;
+  double ax = fabs(x);
+  double r = ax;
+  if (ax >= PI) {
+    double q = floor(__dmul_rn(ax, 0.31830988618379067154));
+    r = __fma_rn(-q, PI, ax);
+    if (r < 0.0) r = __dadd_rn(r, PI);
+    else if (r >= PI) r = __dsub_rn(r, PI);
+  }
+  return copysign(r, x);
+}
+
+// random(), basic_lighting.cl:64-67
+__device__ __forceinline__ float lt_random(float fx, float fy, float seed) {
+  float d = FADD(FMUL(fx, 12.9898f), FMUL(fy, 78.233f));
+  double x = __dadd_rn((double)d, __dmul_rn(1113.1, (double)seed));
+  float a = (float)__dmul_rn(sin(fmod_pi(x)), 43758.5453);
+  return FSUB(a, floorf(a));
+}
+
+__device__ __forceinline__ float len3(float x, float y, float z) {
+  return FSQRT(FADD(FADD(FMUL(x, x), FMUL(y, y)), FMUL(z, z)));
+}
+__device__ __forceinline__ float dot3plain(const float a[3], const float b[3]) {
+  return FADD(FADD(FMUL(a[0], b[0]), FMUL(a[1], b[1])), FMUL(a[2], b[2]));
+}
+// basic_lighting.cl:236-244 / global_illumination.cl:235-240 (no contraction)
+__device__ __forceinline__ void lerp_plain(const float* a, const float* b, const float* c, float w0, float u,
+                                           float v, float out[3]) {
+#pragma unroll
+  for (int k = 0; k < 3; k++) out[k] = FADD(FADD(FMUL(a[k], w0), FMUL(b[k], u)), FMUL(c[k], v));
+}
+
+__device__ __forceinline__ bool is_light(const LtSceneDev& sc, int prim) {
+  bool hit = false;
+  unsigned n = min(sc.lights->count, 64u);
+  for (unsigned x = 0; x < n; x++) hit = hit || ((unsigned)prim == sc.lights->primitives[x]);
+  return hit;
+}
+
+// light sample: basic_lighting.cl:246-262.  Produces the shadow ray; returns its initial t.
+__device__ __forceinline__ float make_shadow_ray(const LtSceneDev& sc, const float pos[3], float fx, float fy,
+                                                 unsigned seedBase, Ray& sr, float toLight[3]) {
+  int idx = (int)FMUL(lt_random(fx, fy, (float)seedBase), (float)sc.lights->count);
+  idx = max(0, min(idx, 63));
+  const RefPrim* lp = sc.prims + sc.lights->primitives[idx];
+  float ux = lt_random(fx, fy, (float)(seedBase + 1u));
+  float uy = lt_random(fx, fy, (float)(seedBase + 2u));
+  if (FADD(ux, uy) > 1.0f) {
+    ux = FSUB(1.0f, ux);
+    uy = FSUB(1.0f, uy);
+  }
+  float w0 = bary0(ux, uy);
+  float Lp[3];
+  lerp_plain(lp->a, lp->b, lp->c, w0, ux, uy, Lp);
+  float dx = FSUB(Lp[0], pos[0]), dy = FSUB(Lp[1], pos[1]), dz = FSUB(Lp[2], pos[2]);
+  float len = len3(dx, dy, dz);
+  toLight[0] = FDIV(dx, len);
+  toLight[1] = FDIV(dy, len);
+  toLight[2] = FDIV(dz, len);
+  sr.ox = pos[0]; sr.oy = pos[1]; sr.oz = pos[2];
+  sr.dx = toLight[0]; sr.dy = toLight[1]; sr.dz = toLight[2];
+  return (float)__dsub_rn((double)len, 0.01);
+}
+
+// uniformSampleHemisphere + alignHemisphereWithCoordinateSystem, global_illumination.cl:69-82
+__device__ __forceinline__ void sample_hemisphere(float u1, float u2, const float up[3], float dir[4]) {
+  float z = u1;
+  float r = FSQRT(fmaxf(0.0f, FSUB(1.0f, FMUL(z, z))));
+  double phi = __dmul_rn(6.28318530717958647692, (double)u2);
+  double sp, cp;
+  sincos(phi, &sp, &cp);
+  float hx = (float)__dmul_rn((double)r, cp);
+  float hy = z;
+  float hz = (float)__dmul_rn((double)r, sp);
+  const float cx = 0.0072f, cy = 1.0f, cz = 0.0034f;
+  float rx = FSUB(FMUL(up[1], cz), FMUL(up[2], cy));
+  float ry = FSUB(FMUL(up[2], cx), FMUL(up[0], cz));
+  float rz = FSUB(FMUL(up[0], cy), FMUL(up[1], cx));
+  float rl = len3(rx, ry, rz);
+  rx = FDIV(rx, rl); ry = FDIV(ry, rl); rz = FDIV(rz, rl);
+  float fwx = FSUB(FMUL(ry, up[2]), FMUL(rz, up[1]));
+  float fwy = FSUB(FMUL(rz, up[0]), FMUL(rx, up[2]));
+  float fwz = FSUB(FMUL(rx, up[1]), FMUL(ry, up[0]));
+  dir[0] = FADD(FADD(FMUL(hx, rx), FMUL(hy, up[0])), FMUL(hz, fwx));
+  dir[1] = FADD(FADD(FMUL(hx, ry), FMUL(hy, up[1])), FMUL(hz, fwy));
+  dir[2] = FADD(FADD(FMUL(hx, rz), FMUL(hy, up[2])), FMUL(hz, fwz));
+  dir[3] = hy;
+}
+
+enum PathStage { ST_PRIMARY = 0, ST_SHADOW_DIRECT = 1, ST_EXTENSION = 2, ST_SHADOW_EXT = 3 };
+
+// One thread = one pixel.  The loop body traces exactly one ray per iteration; what the ray is
+// (primary / shadow / extension) is per-lane state, so lanes at different path depths and
+// different samples still execute the traversal together.
+template <bool STATS>
+__global__ void __launch_bounds__(LT_BLOCK) k_path(LtSceneDev sc, LtLaunch L, float* __restrict__ out,
+                                                   LtCounters* gcnt) {
+  extern __shared__ int smemStack[];
+  int* stk = smemStack + threadIdx.x;
+  int px, py;
+  if (!thread_pixel(L.width, L.height, px, py)) return;
+  LtCounters cnt = {0, 0, 0};
+
+  const float tInit = lt_tinit(L.kernel), epsThr = lt_eps(L.kernel);
+  const bool isGI = (L.kernel == 5 || L.kernel == 6);
+  const bool whiteOnLight = (L.kernel == 4);
+  const int samplesPerFrame = (L.kernel == 3 || L.kernel == 5) ? 25 : 1;
+  const int maxDepth = L.maxRayDepth > 0 ? L.maxRayDepth : 16;
+
+  float fx, fy;
+  const Ray cameraRay = camera_ray(L.cam, px, py, L.width, L.height, fx, fy);
+  long long id = ((long long)py * L.width + px) * L.depth;
+  FrameSink sink;
+  sink.begin(L, out, id);
+
+  int frame = 0, sample = 0;
+  float frameColor[3] = {0.0f, 0.0f, 0.0f};
+
+  // per-sample state
+  int stage = ST_PRIMARY;
+  Ray ray = cameraRay;
+  int ignore = -1;
+  float tStart = tInit;
+  bool anyHit = false;
+  float direct[3], indirect[3];
+  float pos[3], nrm[3], diffuse[3], toLight[3];
+  float prevN[3], extW = 0.0f;
+  Ray ext;
+  int prevPrim = 0, hitPrim = 0, depth = 0;
+  unsigned sampleIndex = (samplesPerFrame == 25) ? L.cam.frameCount * 32u : L.cam.frameCount;
+  direct[0] = direct[1] = direct[2] = 0.0f;
+  indirect[0] = indirect[1] = indirect[2] = 0.0f;
+
+  while (frame < L.frames) {
+    Hit h = {tStart, 0.0f, 0.0f, 0, 0};
+    trace<STATS>(sc, ray, ignore, epsThr, anyHit, h, stk, cnt);
+
+    bool sampleDone = false;
+    bool wantShadow = false;     // next ray: shadow ray from (pos, hitPrim)
+    unsigned shadowSeed = 0;
+
+    if (stage == ST_PRIMARY) {
+      // basic_lighting.cl:230-246 / accumulator.cl:233-238 / global_illumination.cl:255-274
+      bool lightHit = (isGI || whiteOnLight) && is_light(sc, h.prim);
+      if (lightHit) {
+        direct[0] = direct[1] = direct[2] = 1.0f;
+        sampleDone = true;
+      } else if (h.hit == 1) {
+        const RefPrim* prim = sc.prims + h.prim;
+        const RefMaterial* mat = sc.mats + prim->materialIndex;
+        float w0 = bary0(h.u, h.v);
+        lerp_plain(prim->a, prim->b, prim->c, w0, h.u, h.v, pos);
+        lerp_plain(prim->na, prim->nb, prim->nc, w0, h.u, h.v, nrm);
+        diffuse[0] = mat->diffuse[0]; diffuse[1] = mat->diffuse[1]; diffuse[2] = mat->diffuse[2];
+        hitPrim = h.prim;
+        wantShadow = true;
+        shadowSeed = sampleIndex;
+        stage = ST_SHADOW_DIRECT;
+      } else {
+        sampleDone = true;
+      }
+    } else if (stage == ST_SHADOW_DIRECT) {
+      if (h.hit == 0) {  // basic_lighting.cl:272-274
+        float d = dot3plain(toLight, nrm);
+        direct[0] = FMUL(diffuse[0], d); direct[1] = FMUL(diffuse[1], d); direct[2] = FMUL(diffuse[2], d);
+      }
+      if (isGI && maxDepth > 0) {  // global_illumination.cl:300-309
+        float dir[4];
+        sample_hemisphere(lt_random(fx, fy, (float)(sampleIndex + 3u)), lt_random(fx, fy, (float)(sampleIndex + 4u)),
+                          nrm, dir);
+        ext.ox = pos[0]; ext.oy = pos[1]; ext.oz = pos[2];
+        ext.dx = dir[0]; ext.dy = dir[1]; ext.dz = dir[2];
+        extW = dir[3];
+        prevN[0] = nrm[0]; prevN[1] = nrm[1]; prevN[2] = nrm[2];
+        prevPrim = hitPrim;
+        depth = 0;
+        stage = ST_EXTENSION;
+      } else {
+        sampleDone = true;
+      }
+    } else if (stage == ST_EXTENSION) {
+      // global_illumination.cl:310-370
+      float w = (float)__ddiv_rn(1.0, (double)(depth + 1));
+      if (is_light(sc, h.prim)) {
+        float d = FADD(FADD(FADD(FMUL(prevN[0], ext.dx), FMUL(prevN[1], ext.dy)), FMUL(prevN[2], ext.dz)),
+                       FMUL(1.0f, extW));
+        float c = FMUL(FMUL(w, 1.0f), d);
+        indirect[0] = FADD(indirect[0], c); indirect[1] = FADD(indirect[1], c); indirect[2] = FADD(indirect[2], c);
+        depth++;  // ray not advanced: the same hit is found again at the next depth (:320-322)
+        if (depth >= maxDepth) sampleDone = true;
+      } else if (h.hit == 1) {
+        const RefPrim* prim = sc.prims + h.prim;
+        const RefMaterial* mat = sc.mats + prim->materialIndex;
+        float w0 = bary0(h.u, h.v);
+        lerp_plain(prim->a, prim->b, prim->c, w0, h.u, h.v, pos);
+        lerp_plain(prim->na, prim->nb, prim->nc, w0, h.u, h.v, nrm);
+        diffuse[0] = mat->diffuse[0]; diffuse[1] = mat->diffuse[1]; diffuse[2] = mat->diffuse[2];
+        hitPrim = h.prim;
+        wantShadow = true;
+        shadowSeed = sampleIndex + (unsigned)depth + 5u;
+        stage = ST_SHADOW_EXT;
+      } else {
+        sampleDone = true;
+      }
+    } else {  // ST_SHADOW_EXT, global_illumination.cl:352-365
+      if (h.hit == 0) {
+        float w = (float)__ddiv_rn(1.0, (double)(depth + 1));
+        float d = dot3plain(toLight, nrm);
+        indirect[0] = FADD(indirect[0], FMUL(FMUL(w, diffuse[0]), d));
+        indirect[1] = FADD(indirect[1], FMUL(FMUL(w, diffuse[1]), d));
+        indirect[2] = FADD(indirect[2], FMUL(FMUL(w, diffuse[2]), d));
+        float dir[4];
+        sample_hemisphere(lt_random(fx, fy, (float)(sampleIndex + (unsigned)depth + 8u)),
+                          lt_random(fx, fy, (float)(sampleIndex + (unsigned)depth + 9u)), nrm, dir);
+        ext.ox = pos[0]; ext.oy = pos[1]; ext.oz = pos[2];
+        ext.dx = dir[0]; ext.dy = dir[1]; ext.dz = dir[2];
+        extW = dir[3];
+        prevN[0] = nrm[0]; prevN[1] = nrm[1]; prevN[2] = nrm[2];
+        prevPrim = hitPrim;
+        depth++;
+        stage = ST_EXTENSION;
+        if (depth >= maxDepth) sampleDone = true;
+      } else {
+        sampleDone = true;
+      }
+    }
+
+    if (sampleDone) {
+      float c[3] = {FADD(direct[0], indirect[0]), FADD(direct[1], indirect[1]), FADD(direct[2], indirect[2])};
+      if (samplesPerFrame == 1) {
+        frameColor[0] = c[0]; frameColor[1] = c[1]; frameColor[2] = c[2];
+      } else if (sample == 0) {
+        frameColor[0] = c[0]; frameColor[1] = c[1]; frameColor[2] = c[2];
+      } else {  // basic_lighting.cl:310-316: recency-weighted blend
+        float a = FDIV((float)(25 - sample), 25.0f);
+        float ia = FSUB(1.0f, a);
+#pragma unroll
+        for (int k = 0; k < 3; k++) frameColor[k] = FADD(FMUL(ia, frameColor[k]), FMUL(a, c[k]));
+      }
+      sample++;
+      if (sample == samplesPerFrame) {
+        if (samplesPerFrame == 25 && L.kernelMode == 0) {  // clamp only in linearKernel (:318-320)
+#pragma unroll
+          for (int k = 0; k < 3; k++) frameColor[k] = fminf(fmaxf(frameColor[k], 0.0f), 1.0f);
+        }
+        unsigned fc = L.cam.frameCount + (unsigned)frame * L.frameStride;
+        sink.frame(L, fc, frameColor);
+        sample = 0;
+        frame++;
+      }
+      unsigned fcNext = L.cam.frameCount + (unsigned)frame * L.frameStride;
+      sampleIndex = (samplesPerFrame == 25) ? fcNext * 32u + (unsigned)sample : fcNext;
+      direct[0] = direct[1] = direct[2] = 0.0f;
+      indirect[0] = indirect[1] = indirect[2] = 0.0f;
+      stage = ST_PRIMARY;
+      ray = cameraRay;
+      ignore = -1;
+      tStart = tInit;
+      anyHit = false;
+    } else if (wantShadow) {
+      tStart = make_shadow_ray(sc, pos, fx, fy, shadowSeed, ray, toLight);
+      ignore = hitPrim;
+      anyHit = true;
+    } else {  // extension ray
+      ray = ext;
+      ignore = prevPrim;
+      tStart = tInit;
+      anyHit = false;
+    }
+  }
+  sink.end(out, id);
+  if (STATS) flush_counters(gcnt, cnt);
+}
+
+// ------------------------------------------------------------------------------------------------
+// primary hit records (parity/debug output)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(LT_BLOCK) k_primary_hits(LtSceneDev sc, RefCamera cam, int kernel, int width,
+                                                           int height, int* __restrict__ ids, int* __restrict__ hit,
+                                                           float* __restrict__ tuv) {
+  extern __shared__ int smemStack[];
+  int* stk = smemStack + threadIdx.x;
+  int px, py;
+  if (!thread_pixel(width, height, px, py)) return;
+  LtCounters cnt = {0, 0, 0};
+  float fx, fy;
+  Ray ray = camera_ray(cam, px, py, width, height, fx, fy);
+  Hit h = {lt_tinit(kernel), 0.0f, 0.0f, 0, 0};
+  trace<false>(sc, ray, -1, lt_eps(kernel), false, h, stk, cnt);
+  long long i = (long long)py * width + px;
+  if (ids) ids[i] = h.prim;
+  if (hit) hit[i] = h.hit;
+  if (tuv) {
+    tuv[3 * i + 0] = h.t;
+    tuv[3 * i + 1] = h.u;
+    tuv[3 * i + 2] = h.v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// upload-time re-flatten: reference nodes/primitives -> LtWideNode / LtTri (once per scene)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_inner_flags(const RefNode* __restrict__ nodes, int n, int* __restrict__ flags) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flags[i] = nodes[i].primitiveCount == 0 ? 1 : 0;
+}
+
+__global__ void k_build_wide(const RefNode* __restrict__ nodes, int n, const int* __restrict__ innerRank,
+                             LtWideNode* __restrict__ wide) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  RefNode nd = nodes[i];
+  if (nd.primitiveCount != 0) return;
+  int li = i + 1, ri = nd.offset;
+  RefNode l = nodes[li], r = nodes[ri];
+  LtWideNode w;
+  w.bx = make_float4(l.boundsMin[0], l.boundsMax[0], r.boundsMin[0], r.boundsMax[0]);
+  w.by = make_float4(l.boundsMin[1], l.boundsMax[1], r.boundsMin[1], r.boundsMax[1]);
+  w.bz = make_float4(l.boundsMin[2], l.boundsMax[2], r.boundsMin[2], r.boundsMax[2]);
+  int lref = l.primitiveCount > 0 ? ~l.offset : innerRank[li];
+  int rref = r.primitiveCount > 0 ? ~r.offset : innerRank[ri];
+  w.meta = make_int4(lref, rref, (int)nd.axis, (int)((unsigned)l.primitiveCount | ((unsigned)r.primitiveCount << 16)));
+  wide[innerRank[i]] = w;
+}
+
+__global__ void k_build_tris(const RefPrim* __restrict__ prims, int n, LtTri* __restrict__ tris) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const RefPrim* p = prims + i;
+  float ax = p->a[0], ay = p->a[1], az = p->a[2];
+  LtTri t;
+  t.q0 = make_float4(ax, ay, az, FSUB(p->b[0], ax));
+  t.q1 = make_float4(FSUB(p->b[1], ay), FSUB(p->b[2], az), FSUB(p->c[0], ax), FSUB(p->c[1], ay));
+  t.q2 = make_float4(FSUB(p->c[2], az), __int_as_float(p->materialIndex), 0.0f, 0.0f);
+  tris[i] = t;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side launchers
+// ------------------------------------------------------------------------------------------------
+int lt_launch_inner_flags(const RefNode* dNodes, int nodeCount, int* dFlags, cudaStream_t stream) {
+  k_inner_flags<<<(nodeCount + 255) / 256, 256, 0, stream>>>(dNodes, nodeCount, dFlags);
+  return 1;
+}
+
+size_t lt_scan_temp_bytes(int n) {
+  size_t bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, bytes, (const int*)nullptr, (int*)nullptr, n);
+  return bytes;
+}
+
+int lt_launch_exclusive_scan(void* dTemp, size_t tempBytes, const int* dIn, int* dOut, int n, cudaStream_t stream) {
+  cub::DeviceScan::ExclusiveSum(dTemp, tempBytes, dIn, dOut, n, stream);
+  return 1;
+}
+
+int lt_launch_reflatten(const RefNode* dNodes, int nodeCount, const RefPrim* dPrims, int primCount,
+                        const int* dInnerRank, LtWideNode* dWide, LtTri* dTris, cudaStream_t stream) {
+  k_build_wide<<<(nodeCount + 255) / 256, 256, 0, stream>>>(dNodes, nodeCount, dInnerRank, dWide);
+  k_build_tris<<<(primCount + 255) / 256, 256, 0, stream>>>(dPrims, primCount, dTris);
+  return 2;
+}
+
+static size_t stack_bytes(const LtSceneDev& sc) {
+  int d = sc.stackDepth < 1 ? 1 : sc.stackDepth;
+  return (size_t)d * LT_BLOCK * sizeof(int);
+}
+
+static int tile_blocks(int width, int height) { return ((width + 15) / 16) * ((height + 7) / 8); }
+
+int lt_launch_render(const LtSceneDev& sc, const LtLaunch& L, float* dOut, LtCounters* dCounters,
+                     cudaStream_t stream) {
+  int blocks = tile_blocks(L.width, L.height);
+  size_t smem = stack_bytes(sc);
+  bool stats = (L.flags & 1) != 0;
+  bool flat = (L.kernel <= 2);
+  if (flat) {
+    if (stats) k_flat<true><<<blocks, LT_BLOCK, smem, stream>>>(sc, L, dOut, dCounters);
+    else k_flat<false><<<blocks, LT_BLOCK, smem, stream>>>(sc, L, dOut, nullptr);
+  } else {
+    if (stats) k_path<true><<<blocks, LT_BLOCK, smem, stream>>>(sc, L, dOut, dCounters);
+    else k_path<false><<<blocks, LT_BLOCK, smem, stream>>>(sc, L, dOut, nullptr);
+  }
+  return 1;
+}
+
+int lt_launch_primary_hits(const LtSceneDev& sc, const RefCamera& cam, int kernel, int width, int height,
+                           int* dIds, int* dHit, float* dTuv, cudaStream_t stream) {
+  k_primary_hits<<<tile_blocks(width, height), LT_BLOCK, stack_bytes(sc), stream>>>(sc, cam, kernel, width, height,
+                                                                                    dIds, dHit, dTuv);
+  return 1;
+}

@@ -1,0 +1,150 @@
+// acceleration_structure_explicit.cpp -- deterministic median-split BVH, emitted directly in the
+// reference's flattened DFS layout (see the header for the list of deliberate differences).
+// Split rule, leaf rule and ordering follow src/acceleration_structure_explicit.cpp:47-137:
+//   bounds = union of the primitive bounds; one primitive -> leaf; otherwise take the axis with the
+//   strictly largest centroid extent (x if it beats both, else y if it beats z, else z);
+//   std::nth_element at (start+end)/2 on the centroid of that axis, left = [start,mid),
+//   right = [mid,end).  Equal centroids on that axis: see the comment in build().
+#include "lens_trace/acceleration_structure_explicit.h"
+
+#include <float.h>
+#include <stdio.h>
+
+namespace {
+
+struct BuildItem {
+  float centroid[3];
+  uint32_t source;  // index into the model's primitive list
+};
+
+struct Builder {
+  const std::vector<PrimitiveInfo>& prims;
+  std::vector<BuildItem> items;
+  std::vector<LinearBVHNode>& nodes;
+  std::vector<uint32_t> order;  // leaf order -> source primitive
+
+  Builder(const std::vector<PrimitiveInfo>& p, std::vector<LinearBVHNode>& n) : prims(p), nodes(n) {
+    items.resize(p.size());
+    for (size_t i = 0; i < p.size(); i++) {
+      memcpy(items[i].centroid, p[i].centroid, sizeof(float) * 3);
+      items[i].source = (uint32_t)i;
+    }
+    nodes.reserve(p.size() * 2);
+    order.reserve(p.size());
+  }
+
+  int emitLeaf(int self, int start, int end) {
+    nodes[self].primitivesOffset = (int)order.size();
+    nodes[self].primitiveCount = (uint16_t)(end - start);
+    nodes[self].axis = 0;
+    for (int i = start; i < end; i++) order.push_back(items[i].source);
+    return self;
+  }
+
+  int build(int start, int end) {
+    int self = (int)nodes.size();
+    nodes.push_back(LinearBVHNode());
+    {
+      LinearBVHNode& n = nodes[self];
+      memset(&n, 0, sizeof n);
+      const PrimitiveInfo& first = prims[items[start].source];
+      memcpy(n.boundsMin, first.boundsMin, sizeof(float) * 3);
+      memcpy(n.boundsMax, first.boundsMax, sizeof(float) * 3);
+      for (int i = start; i < end; i++) {
+        const PrimitiveInfo& p = prims[items[i].source];
+        for (int k = 0; k < 3; k++) {
+          n.boundsMin[k] = std::min(n.boundsMin[k], p.boundsMin[k]);
+          n.boundsMax[k] = std::max(n.boundsMax[k], p.boundsMax[k]);
+        }
+      }
+    }
+    if (end - start == 1) return emitLeaf(self, start, end);
+
+    float cmin[3] = {FLT_MAX, FLT_MAX, FLT_MAX};
+    float cmax[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for (int i = start; i < end; i++)
+      for (int k = 0; k < 3; k++) {
+        cmin[k] = std::min(cmin[k], items[i].centroid[k]);
+        cmax[k] = std::max(cmax[k], items[i].centroid[k]);
+      }
+    float extent[3] = {cmax[0] - cmin[0], cmax[1] - cmin[1], cmax[2] - cmin[2]};
+    int dim = (extent[0] > extent[1] && extent[0] > extent[2]) ? 0 : (extent[1] > extent[2] ? 1 : 2);
+    int mid = (start + end) / 2;
+    // Coincident centroids: the reference text would emit one multi-primitive leaf here, but its
+    // kernels only ever test the first primitive of such a leaf (basic.cu:168-172), so triangles
+    // would vanish -- and with its uninitialised bounds the reference in practice keeps splitting
+    // (its own known-answer test, tests/cuda_renderer_test.cc:182-225, needs both green_wall
+    // triangles reachable).  Split by index order instead; every leaf holds one primitive.
+    if (cmax[dim] != cmin[dim])
+      std::nth_element(items.begin() + start, items.begin() + mid, items.begin() + end,
+                       [dim](const BuildItem& a, const BuildItem& b) { return a.centroid[dim] < b.centroid[dim]; });
+    nodes[self].axis = (uint8_t)dim;
+    nodes[self].primitiveCount = 0;
+    build(start, mid);
+    int right = build(mid, end);
+    nodes[self].secondChildOffset = right;
+    return self;
+  }
+};
+
+}  // namespace
+
+AccelerationStructureExplicit::AccelerationStructureExplicit(
+    AccelerationStructureExplicitProperties accelerationStructureExplicitProperties) {
+  Model* pModel = (Model*)accelerationStructureExplicitProperties.pModel;
+  std::vector<PrimitiveInfo>& infos = *pModel->getPrimitiveInfoListP();
+  const Material* materials = (const Material*)pModel->getMaterialBuffer();
+  const size_t materialCount = pModel->getMaterialBufferSize() / sizeof(Material);
+  memset(&lightContainer, 0, sizeof lightContainer);
+  if (infos.empty()) return;
+
+  Builder b(infos, linearNodes);
+  b.build(0, (int)infos.size());
+
+  orderedPrimitives.resize(infos.size());
+  std::vector<PrimitiveInfo> reordered(infos.size());
+  for (size_t x = 0; x < b.order.size(); x++) {
+    const PrimitiveInfo& src = infos[b.order[x]];
+    reordered[x] = src;
+    Primitive& dst = orderedPrimitives[x];
+    memcpy(dst.positionA, src.positionA, sizeof(float) * 3);
+    memcpy(dst.positionB, src.positionB, sizeof(float) * 3);
+    memcpy(dst.positionC, src.positionC, sizeof(float) * 3);
+    memcpy(dst.normalA, src.normalA, sizeof(float) * 3);
+    memcpy(dst.normalB, src.normalB, sizeof(float) * 3);
+    memcpy(dst.normalC, src.normalC, sizeof(float) * 3);
+    dst.materialIndex = src.materialIndex;
+    if (src.materialIndex >= 0 && (size_t)src.materialIndex < materialCount) {
+      const Material& m = materials[src.materialIndex];
+      if (m.emission[0] > 0 || m.emission[1] > 0 || m.emission[2] > 0) {
+        if (lightContainer.count < 64) {
+          lightContainer.primitives[lightContainer.count] = (uint32_t)x;
+          lightContainer.count += 1;
+        } else {
+          static bool warned = false;
+          if (!warned) printf("WARNING: more than 64 emissive primitives; extra lights ignored\n");
+          warned = true;
+        }
+      }
+    }
+  }
+  // like the reference's in-place nth_element, leave the model's list in leaf order
+  infos.swap(reordered);
+}
+
+AccelerationStructureExplicit::~AccelerationStructureExplicit() {}
+
+uint64_t AccelerationStructureExplicit::getNodeBufferSize() { return sizeof(LinearBVHNode) * linearNodes.size(); }
+void* AccelerationStructureExplicit::getNodeBuffer() { return linearNodes.data(); }
+
+uint64_t AccelerationStructureExplicit::getOrderedPrimitiveBufferSize() {
+  return sizeof(Primitive) * orderedPrimitives.size();
+}
+void* AccelerationStructureExplicit::getOrderedPrimitiveBuffer() { return orderedPrimitives.data(); }
+
+uint64_t AccelerationStructureExplicit::getLightContainerBufferSize() { return sizeof(LightContainer); }
+void* AccelerationStructureExplicit::getLightContainerBuffer() { return &this->lightContainer; }
+
+static_assert(sizeof(LinearBVHNode) == 32, "LinearBVHNode must stay 32 bytes");
+static_assert(sizeof(Primitive) == 76, "Primitive must stay 76 bytes");
+static_assert(sizeof(LightContainer) == 260, "LightContainer must stay 260 bytes");

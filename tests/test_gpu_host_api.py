@@ -1,0 +1,112 @@
+"""The reference's five renderer tests (tests/cuda_renderer_test.cc, tests/opencl_renderer_test.cc),
+re-expressed against this repo's RendererCUDA / RendererOpenCL through the C++ host surface."""
+import os
+
+import numpy as np
+import pytest
+
+import lt_oracle as O
+import util
+from lens_trace_b200 import host, layouts as L
+
+pytestmark = pytest.mark.gpu
+
+CU = "resources/kernels/cuda/basic.cu"
+CL = "resources/kernels/opencl/basic.cl"
+
+
+@pytest.fixture(scope="module")
+def world():
+    os.chdir(util.ROOT)  # resource paths are CWD-relative (src/resource.cpp:3-16)
+    cam = host.Camera(0, 2.5, -50, 0)
+    model = host.Model("resources/models/green_wall.obj")
+    accel = host.AccelerationStructure(model)
+    yield cam, model, accel
+    accel.close()
+    model.close()
+    cam.close()
+
+
+@pytest.mark.parametrize("platform,kernel", [(host.PLATFORM_CUDA, CU), (host.PLATFORM_OPENCL, CL)])
+def test_create_engine_and_valid_buffer(world, platform, kernel):
+    cam, model, accel = world
+    r = host.Renderer(platform)  # CreateEngineTEST.ValidEngine
+    assert r.h
+    out = r.render(kernel, 100, 100, accel, model, cam)  # RenderBufferTEST.ValidBuffer
+    assert out.shape == (100, 100, 3)
+    r.close()
+
+
+@pytest.mark.parametrize("platform,kernel", [(host.PLATFORM_CUDA, CU), (host.PLATFORM_OPENCL, CL)])
+def test_custom_block_size(world, platform, kernel):
+    cam, model, accel = world
+    r = host.Renderer(platform)
+    a = r.render(kernel, 100, 100, accel, model, cam).reshape(-1)
+    b = r.render(kernel, 100, 100, accel, model, cam, block=(8, 8)).reshape(-1)
+    c = r.render(kernel, 100, 100, accel, model, cam, block=(4, 4)).reshape(-1)
+    for x in range(0, 100 * 100, 32):  # tests/cuda_renderer_test.cc:106-109
+        assert a[x] == b[x] == c[x]
+    r.close()
+
+
+@pytest.mark.parametrize("platform,kernel", [(host.PLATFORM_CUDA, CU), (host.PLATFORM_OPENCL, CL)])
+def test_kernel_mode(world, platform, kernel):
+    cam, model, accel = world
+    r = host.Renderer(platform)
+    a = r.render(kernel, 100, 100, accel, model, cam, kernel_mode=0).reshape(-1)
+    b = r.render(kernel, 100, 100, accel, model, cam, kernel_mode=1).reshape(-1)
+    for x in range(0, 100 * 100 * 3, 32):  # tests/cuda_renderer_test.cc:173-175
+        assert a[x] == b[x]
+    r.close()
+
+
+@pytest.mark.parametrize("platform,kernel", [(host.PLATFORM_CUDA, CU), (host.PLATFORM_OPENCL, CL)])
+def test_correct_color(world, platform, kernel):
+    cam, model, accel = world
+    r = host.Renderer(platform)
+    flat = r.render(kernel, 100, 100, accel, model, cam).reshape(-1)
+    for x in range(0, 100 * 100, 8 * 3):  # tests/cuda_renderer_test.cc:217-221
+        assert flat[x] == 0.0 and flat[x + 1] == 1.0 and flat[x + 2] == 0.0
+    r.close()
+
+
+def test_examples_flow_progressive_accumulation():
+    """examples/global_illumination/src/main.cpp:269-340 without the GL window: RendererOpenCL, the
+    example's kernel path, frameCount protocol, running mean kept on the device."""
+    os.chdir(util.ROOT)
+    cam = host.Camera(0, 2.5, -50, 0)
+    model = host.Model("resources/models/cornell_box.obj")
+    accel = host.AccelerationStructure(model)
+    r = host.Renderer(host.PLATFORM_OPENCL)
+    kernel = "examples/global_illumination/resources/kernels/global_illumination.cl"
+    w, h, frames = 96, 72, 5
+    ext = host.make_extension(frames=frames, accumulate=True, max_ray_depth=4, collect_stats=True)
+    got = r.render(kernel, w, h, accel, model, cam, ext=ext)
+    sb = accel.buffers()
+    acc = np.zeros((h, w, 3), np.float32)
+    for f in range(frames):
+        O.accumulate(acc, O.render(L.KERNEL_GI, sb, util.default_camera(0.0, f), w, h, max_ray_depth=4, threads=0), f)
+    bad = (util.bits(got) != util.bits(acc)).any(axis=-1)
+    assert bad.sum() <= 3
+    np.testing.assert_allclose(got, acc, rtol=1e-4, atol=1e-6)
+    assert ext.rays >= frames * w * h and ext.kernelMilliseconds > 0
+    # an unknown kernel file is a reported error and leaves the buffer untouched
+    out = np.full((h, w, 3), -1, np.float32)
+    r.render("resources/kernels/opencl/not_a_kernel.cl", w, h, accel, model, cam, out=out)
+    assert (out == -1).all()
+    r.close()
+    accel.close()
+    model.close()
+    cam.close()
+
+
+def test_scene_file_end_to_end():
+    import ctypes as C
+    os.chdir(util.ROOT)
+    out = np.zeros((2048, 2048, 3), np.float32)
+    dims = (C.c_uint64 * 3)()
+    rc = host.load().lth_run_scene_file(b"resources/scenes/basic_cuda.scene", out.ctypes.data, out.nbytes, C.byref(dims))
+    assert rc == 0 and tuple(dims) == (2048, 2048, 3)
+    want = O.render(L.KERNEL_BASIC_CU, util.scene("cornell_box"), util.default_camera(), 2048, 2048, rows=(1000, 1016),
+                    threads=0)
+    util.assert_bit_equal(out[1000:1016], want[1000:1016])

@@ -1,0 +1,222 @@
+"""GPU parity tests: the CUDA path, called through the C-ABI, against the CPU oracle on the same
+buffers.  Bar: bit-exact for primitive ids / hit flags, and bit-exact FP32 for every deterministic
+pass (tolerance only where the fp64 device sin/cos of the hash RNG may differ from libm in the last
+place: at most a handful of pixels, each checked to 1e-4 relative)."""
+import numpy as np
+import pytest
+
+import lt_oracle as O
+import util
+from lens_trace_b200 import capi, layouts as L
+
+pytestmark = pytest.mark.gpu
+
+FLAVOUR = {L.KERNEL_BASIC_CU: 0, L.KERNEL_BASIC_CL: 1, L.KERNEL_CUSTOM_BARY: 1, L.KERNEL_LIGHTING25: 1,
+           L.KERNEL_ACCUMULATOR: 2, L.KERNEL_GI25: 2, L.KERNEL_GI: 2}
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+_uploaded = {}
+
+
+def gpu_scene(ctx, name):
+    if name not in _uploaded:
+        sb = {"single": util.single_triangle_scene, "single_light": lambda: util.single_triangle_scene(True),
+              "multi_leaf": util.multi_prim_leaf_scene}.get(name, lambda: util.scene(name))()
+        _uploaded[name] = (sb, ctx.upload(sb))
+    return _uploaded[name]
+
+
+def assert_images_match(got, want, what, max_outliers=0):
+    """bit-exact, except for at most max_outliers pixels which must still agree to 1e-4 relative"""
+    gb, wb = util.bits(got), util.bits(want)
+    bad = (gb != wb).any(axis=-1)
+    n = int(bad.sum())
+    if n == 0:
+        return
+    assert n <= max_outliers, "%s: %d pixels differ bitwise (allowed %d)" % (what, n, max_outliers)
+    np.testing.assert_allclose(got[bad], want[bad], rtol=1e-4, atol=1e-6, err_msg=what)
+
+
+@pytest.mark.parametrize("name", ["green_wall", "cornell_box", "cornell_box_lens", "single", "multi_leaf"])
+@pytest.mark.parametrize("size", [(100, 100), (33, 17), (1, 1), (257, 130)])
+@pytest.mark.parametrize("yaw", [0.0, 0.3, -2.5])
+def test_primary_hit_records_bit_exact(ctx, name, size, yaw):
+    sb, sc = gpu_scene(ctx, name)
+    cam = util.default_camera(yaw)
+    w, h = size
+    for kernel in (L.KERNEL_BASIC_CU, L.KERNEL_GI):
+        ids, hit, tuv = ctx.primary_hits(sc, cam, kernel, w, h)
+        oids, ohit, otuv, _ = O.primary_hits(FLAVOUR[kernel], sb, cam, w, h)
+        np.testing.assert_array_equal(hit, ohit)
+        np.testing.assert_array_equal(ids, oids)
+        util.assert_bit_equal(tuv, otuv, "%s t,u,v" % name)
+
+
+@pytest.mark.parametrize("kernel", [L.KERNEL_BASIC_CU, L.KERNEL_BASIC_CL, L.KERNEL_CUSTOM_BARY])
+@pytest.mark.parametrize("name", ["green_wall", "cornell_box", "cornell_box_lens", "single"])
+@pytest.mark.parametrize("yaw", [0.0, 0.2])
+def test_deterministic_kernels_bit_exact(ctx, kernel, name, yaw):
+    sb, sc = gpu_scene(ctx, name)
+    cam = util.default_camera(yaw)
+    for w, h, mode in ((100, 100, 0), (161, 75, 1)):
+        got = ctx.render(sc, cam, capi.make_params(kernel, w, h, kernel_mode=mode))
+        want = O.render(kernel, sb, cam, w, h, kernel_mode=mode)
+        util.assert_bit_equal(got, want, "%s kernel %d" % (name, kernel))
+
+
+def test_reference_known_answer_on_gpu(ctx):
+    # tests/cuda_renderer_test.cc:182-225
+    sb, sc = gpu_scene(ctx, "green_wall")
+    flat = ctx.render(sc, util.default_camera(), capi.make_params(L.KERNEL_BASIC_CU, 100, 100)).reshape(-1)
+    for x in range(0, 100 * 100, 8 * 3):
+        assert flat[x] == 0.0 and flat[x + 1] == 1.0 and flat[x + 2] == 0.0
+
+
+@pytest.mark.parametrize("kernel,depth", [(L.KERNEL_ACCUMULATOR, 0), (L.KERNEL_GI, 4), (L.KERNEL_GI, 16),
+                                          (L.KERNEL_GI, 1)])
+@pytest.mark.parametrize("name", ["cornell_box", "cornell_box_lens", "single_light"])
+@pytest.mark.parametrize("frame", [0, 1, 7, 63])
+def test_stochastic_single_sample(ctx, kernel, depth, name, frame):
+    sb, sc = gpu_scene(ctx, name)
+    cam = util.default_camera(0.0, frame)
+    w, h = 128, 96
+    got = ctx.render(sc, cam, capi.make_params(kernel, w, h, max_ray_depth=depth))
+    want = O.render(kernel, sb, cam, w, h, max_ray_depth=depth if depth else 16, threads=0)
+    assert np.isfinite(got).all()
+    assert_images_match(got, want, "kernel %d frame %d" % (kernel, frame), max_outliers=3)
+
+
+@pytest.mark.parametrize("kernel", [L.KERNEL_LIGHTING25, L.KERNEL_GI25])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_blend25_kernels(ctx, kernel, mode):
+    sb, sc = gpu_scene(ctx, "cornell_box")
+    cam = util.default_camera(0.1, 2)
+    got = ctx.render(sc, cam, capi.make_params(kernel, 64, 48, kernel_mode=mode, max_ray_depth=3))
+    want = O.render(kernel, sb, cam, 64, 48, kernel_mode=mode, max_ray_depth=3, threads=0)
+    assert_images_match(got, want, "blend25 kernel %d" % kernel, max_outliers=3)
+
+
+def test_running_mean_matches_frame_by_frame_protocol(ctx):
+    """examples/global_illumination/src/main.cpp:296-325: one sample per frame, frameCount = 0,1,2..,
+    running mean.  One multi-frame launch == the oracle rendering frame by frame and accumulating."""
+    sb, sc = gpu_scene(ctx, "cornell_box")
+    w, h, frames = 96, 64, 6
+    p = capi.make_params(L.KERNEL_GI, w, h, max_ray_depth=4, frames=frames, accum_mode=L.ACCUM_RUNNING_MEAN)
+    got = ctx.render(sc, util.default_camera(0.0, 0), p)
+    acc = np.zeros((h, w, 3), np.float32)
+    for f in range(frames):
+        O.accumulate(acc, O.render(L.KERNEL_GI, sb, util.default_camera(0.0, f), w, h, max_ray_depth=4, threads=0), f)
+    assert_images_match(got, acc, "running mean", max_outliers=3)
+    # the same through successive single-frame calls sharing the context accumulator
+    ctx.accum_reset()
+    for f in range(frames):
+        p1 = capi.make_params(L.KERNEL_GI, w, h, max_ray_depth=4, frames=1, accum_mode=L.ACCUM_RUNNING_MEAN)
+        step = ctx.render(sc, util.default_camera(0.0, f), p1)
+    util.assert_bit_equal(step, got, "multi-frame launch vs frame-by-frame launches")
+
+
+def test_accumulating_a_deterministic_kernel(ctx):
+    # BASELINE config 4: custom kernel, 16 accumulated frames
+    sb, sc = gpu_scene(ctx, "cornell_box")
+    w, h = 120, 80
+    p = capi.make_params(L.KERNEL_CUSTOM_BARY, w, h, frames=16, accum_mode=L.ACCUM_RUNNING_MEAN)
+    got = ctx.render(sc, util.default_camera(), p)
+    one = O.render(L.KERNEL_CUSTOM_BARY, sb, util.default_camera(), w, h)
+    acc = np.zeros_like(one)
+    for f in range(16):
+        O.accumulate(acc, one, f)
+    util.assert_bit_equal(got, acc)
+    np.testing.assert_allclose(got, one, rtol=1e-6, atol=1e-7)
+
+
+def test_weighted_sum_split_equals_mean(ctx):
+    # sample split across G "ranks": rank g renders frames g, g+G, .. weighted 1/N; the sum is the mean
+    sb, sc = gpu_scene(ctx, "cornell_box")
+    w, h, n, g = 64, 64, 8, 4
+    total = np.zeros((h, w, 3), np.float64)
+    for r in range(g):
+        ctx.accum_reset()
+        p = capi.make_params(L.KERNEL_ACCUMULATOR, w, h, frames=n // g, frame_stride=g,
+                             accum_mode=L.ACCUM_WEIGHTED_SUM, accum_weight=1.0 / n)
+        total += ctx.render(sc, util.default_camera(0.0, r), p)
+    ctx.accum_reset()
+    mean = ctx.render(sc, util.default_camera(0.0, 0),
+                      capi.make_params(L.KERNEL_ACCUMULATOR, w, h, frames=n, accum_mode=L.ACCUM_RUNNING_MEAN))
+    np.testing.assert_allclose(total, mean, rtol=1e-5, atol=1e-6)
+
+
+def test_stats_count_the_reference_traversal(ctx):
+    for name, kernel, depth in (("cornell_box", L.KERNEL_BASIC_CU, 0), ("cornell_box_lens", L.KERNEL_BASIC_CU, 0),
+                                ("cornell_box", L.KERNEL_GI, 4), ("multi_leaf", L.KERNEL_BASIC_CU, 0)):
+        sb, sc = gpu_scene(ctx, name)
+        cam = util.default_camera(0.0, 1)
+        ctx.render(sc, cam, capi.make_params(kernel, 96, 96, max_ray_depth=depth, flags=L.FLAG_STATS))
+        st = ctx.stats()
+        _, ost = O.render(kernel, sb, cam, 96, 96, max_ray_depth=depth if depth else 16, with_stats=True, threads=0)
+        assert (st.rays, st.node_tests, st.tri_tests) == (ost.rays, ost.nodeTests, ost.triTests), name
+
+
+def test_stats_mode_does_not_change_the_image(ctx):
+    sb, sc = gpu_scene(ctx, "cornell_box")
+    cam = util.default_camera(0.0, 5)
+    a = ctx.render(sc, cam, capi.make_params(L.KERNEL_GI, 80, 60, max_ray_depth=4))
+    b = ctx.render(sc, cam, capi.make_params(L.KERNEL_GI, 80, 60, max_ray_depth=4, flags=L.FLAG_STATS))
+    util.assert_bit_equal(a, b)
+
+
+def test_synthetic_mesh_parity(ctx, tmp_path):
+    from lens_trace_b200 import host
+    p = str(tmp_path / "synth.obj")
+    host.write_synthetic_scene(p, 96, 0x5EED)  # 18 444 triangles
+    sb = host.load_scene_buffers(p)
+    sc = ctx.upload(sb)
+    cam = util.default_camera()
+    ids, hit, tuv = ctx.primary_hits(sc, cam, L.KERNEL_GI, 200, 120)
+    oids, ohit, otuv, _ = O.primary_hits(2, sb, cam, 200, 120)
+    np.testing.assert_array_equal(hit, ohit)
+    np.testing.assert_array_equal(ids, oids)
+    util.assert_bit_equal(tuv, otuv)
+    got = ctx.render(sc, util.default_camera(0.0, 3), capi.make_params(L.KERNEL_GI, 160, 90, max_ray_depth=4))
+    want = O.render(L.KERNEL_GI, sb, util.default_camera(0.0, 3), 160, 90, max_ray_depth=4, threads=0)
+    assert_images_match(got, want, "synthetic GI", max_outliers=3)
+    sc.release()
+
+
+def test_full_size_properties(ctx):
+    """1080p, BASELINE config 2 size: properties that need no oracle run."""
+    sb, sc = gpu_scene(ctx, "cornell_box")
+    w, h = 1920, 1080
+    lin = ctx.render(sc, util.default_camera(), capi.make_params(L.KERNEL_BASIC_CU, w, h, kernel_mode=0))
+    til = ctx.render(sc, util.default_camera(), capi.make_params(L.KERNEL_BASIC_CU, w, h, kernel_mode=1))
+    util.assert_bit_equal(lin, til, "linear vs tile")  # tests/cuda_renderer_test.cc:117-180
+    # a sub-window of the full-size image equals the oracle on those rows
+    want = O.render(L.KERNEL_BASIC_CU, sb, util.default_camera(), w, h, rows=(500, 540), threads=0)
+    util.assert_bit_equal(lin[500:540], want[500:540], "rows 500-540 at 1080p")
+    # GI: 2 frames in one launch == 2 launches; band check against the oracle
+    ctx.accum_reset()
+    p2 = capi.make_params(L.KERNEL_GI, w, h, max_ray_depth=4, frames=2, accum_mode=L.ACCUM_RUNNING_MEAN)
+    two = ctx.render(sc, util.default_camera(0.0, 0), p2)
+    acc = np.zeros((h, w, 3), np.float32)
+    for f in range(2):
+        O.accumulate(acc, O.render(L.KERNEL_GI, sb, util.default_camera(0.0, f), w, h, max_ray_depth=4,
+                                   rows=(600, 620), threads=0), f)
+    assert_images_match(two[600:620], acc[600:620], "GI rows 600-620 at 1080p", max_outliers=3)
+
+
+def test_bad_arguments_are_errors(ctx):
+    sb, sc = gpu_scene(ctx, "cornell_box")
+    with pytest.raises(capi.LtError):
+        ctx.render(sc, util.default_camera(), capi.make_params(99, 10, 10))
+    with pytest.raises(capi.LtError):
+        ctx.render(sc, util.default_camera(), capi.make_params(L.KERNEL_BASIC_CU, 0, 10))
+    bad = L.SceneBuffers(sb.nodes.copy(), sb.prims.copy(), sb.materials.copy(), sb.lights.copy())
+    bad.nodes["offset"][0] = 10 ** 6
+    with pytest.raises(capi.LtError):
+        ctx.upload(bad)
