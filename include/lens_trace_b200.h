@@ -132,6 +132,12 @@ int lt_primary_hits(lt_ctx* ctx, lt_scene* scene, const void* camera28, int kern
 
 int lt_last_stats(const lt_ctx* ctx, lt_stats* out_stats);
 
+/* Parity hooks (host pointers): the device's evaluation of random() (basic_lighting.cl:64-67) and of
+ * alignHemisphereWithCoordinateSystem(uniformSampleHemisphere(u1,u2), up) (global_illumination.cl:69-82;
+ * up3 = 3 floats per sample, out4 = 4 floats per sample), for tests that pin them against the oracle. */
+int lt_debug_random(lt_ctx* ctx, const float* fx, const float* fy, const float* seed, int n, float* out);
+int lt_debug_hemisphere(lt_ctx* ctx, const float* u1, const float* u2, const float* up3, int n, float* out4);
+
 /* Maps RenderProperties*::kernelFilePath to an lt_kernel by the file's base name and, when the file
  * is readable, its defining text (SAMPLE_COUNT, epsilon); returns LT_ERR_UNSUPPORTED for a file that
  * is not one of the shipped kernels. */

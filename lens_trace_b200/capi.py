@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "liblt_b200.so")
 SYMBOLS = [
     "lt_api_version", "lt_ctx_create", "lt_ctx_destroy", "lt_last_error", "lt_ctx_set_stream", "lt_scene_upload",
     "lt_scene_release", "lt_render", "lt_render_device", "lt_accum_reset", "lt_accum_read", "lt_primary_hits",
-    "lt_last_stats", "lt_kernel_from_path", "lt_kernel_name",
+    "lt_last_stats", "lt_kernel_from_path", "lt_kernel_name", "lt_debug_random", "lt_debug_hemisphere",
 ]
 
 
@@ -70,6 +70,8 @@ def load():
     lib.lt_primary_hits.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                     C.c_void_p, C.c_void_p]
     lib.lt_last_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+    lib.lt_debug_random.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    lib.lt_debug_hemisphere.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     lib.lt_kernel_from_path.argtypes = [C.c_char_p]
     lib.lt_kernel_name.argtypes = [C.c_int]
     lib.lt_kernel_name.restype = C.c_char_p
@@ -162,6 +164,20 @@ class Context:
         self._check(self.lib.lt_primary_hits(self.h, scene.h, cam.ctypes.data, kernel, width, height, ids.ctypes.data,
                                              hit.ctypes.data, tuv.ctypes.data), "lt_primary_hits")
         return ids, hit, tuv
+
+    def debug_random(self, fx, fy, seed):
+        fx, fy, seed = (np.ascontiguousarray(a, dtype=np.float32) for a in (fx, fy, seed))
+        out = np.empty_like(fx)
+        self._check(self.lib.lt_debug_random(self.h, fx.ctypes.data, fy.ctypes.data, seed.ctypes.data, fx.size,
+                                             out.ctypes.data), "lt_debug_random")
+        return out
+
+    def debug_hemisphere(self, u1, u2, up):
+        u1, u2, up = (np.ascontiguousarray(a, dtype=np.float32) for a in (u1, u2, up))
+        out = np.empty((u1.size, 4), dtype=np.float32)
+        self._check(self.lib.lt_debug_hemisphere(self.h, u1.ctypes.data, u2.ctypes.data, up.ctypes.data, u1.size,
+                                                 out.ctypes.data), "lt_debug_hemisphere")
+        return out
 
     def stats(self):
         s = Stats()

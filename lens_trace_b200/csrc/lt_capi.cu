@@ -5,6 +5,7 @@
 #include "lt_internal.h"
 
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -270,6 +271,17 @@ static int check_params(lt_ctx* ctx, const lt_scene* scene, const void* camera28
   L->accumMode = p->accum_mode;
   L->accumWeight = p->accum_weight;
   L->flags = p->flags;
+  {
+    // tuning knob (not part of the ABI): lanes below which a warp regenerates rays
+    static int threshold = -1;
+    if (threshold < 0) {
+      const char* e = getenv("LT_REFILL_THRESHOLD");
+      threshold = e ? atoi(e) : 20;
+      if (threshold < 1) threshold = 1;
+      if (threshold > 32) threshold = 32;
+    }
+    L->refillThreshold = threshold;
+  }
   memcpy(&L->cam, camera28, sizeof(RefCamera));
   return LT_OK;
 }
@@ -372,6 +384,39 @@ extern "C" int lt_primary_hits(lt_ctx* ctx, lt_scene* scene, const void* camera2
   cudaFree(dHit);
   cudaFree(dTuv);
   if (e != cudaSuccess) return fail(ctx, LT_ERR_CUDA, std::string("lt_primary_hits: ") + cudaGetErrorString(e));
+  return LT_OK;
+}
+
+// parity hooks: evaluate device-side helper functions on host-supplied inputs
+extern "C" int lt_debug_random(lt_ctx* ctx, const float* fx, const float* fy, const float* seed, int n, float* out) {
+  if (!ctx || !fx || !fy || !seed || !out || n <= 0) return fail(ctx, LT_ERR_INVALID, "lt_debug_random: bad argument");
+  CK(cudaSetDevice(ctx->device));
+  float* d = nullptr;
+  CK(cudaMalloc(&d, sizeof(float) * 4 * (size_t)n));
+  cudaMemcpy(d, fx, sizeof(float) * n, cudaMemcpyHostToDevice);
+  cudaMemcpy(d + n, fy, sizeof(float) * n, cudaMemcpyHostToDevice);
+  cudaMemcpy(d + 2 * (size_t)n, seed, sizeof(float) * n, cudaMemcpyHostToDevice);
+  lt_launch_debug_random(d, d + n, d + 2 * (size_t)n, n, d + 3 * (size_t)n, ctx->stream);
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpy(out, d + 3 * (size_t)n, sizeof(float) * n, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(ctx, LT_ERR_CUDA, std::string("lt_debug_random: ") + cudaGetErrorString(e));
+  return LT_OK;
+}
+
+extern "C" int lt_debug_hemisphere(lt_ctx* ctx, const float* u1, const float* u2, const float* up3, int n, float* out4) {
+  if (!ctx || !u1 || !u2 || !up3 || !out4 || n <= 0) return fail(ctx, LT_ERR_INVALID, "lt_debug_hemisphere: bad argument");
+  CK(cudaSetDevice(ctx->device));
+  float* d = nullptr;
+  CK(cudaMalloc(&d, sizeof(float) * 9 * (size_t)n));
+  cudaMemcpy(d, u1, sizeof(float) * n, cudaMemcpyHostToDevice);
+  cudaMemcpy(d + n, u2, sizeof(float) * n, cudaMemcpyHostToDevice);
+  cudaMemcpy(d + 2 * (size_t)n, up3, sizeof(float) * 3 * n, cudaMemcpyHostToDevice);
+  lt_launch_debug_hemisphere(d, d + n, d + 2 * (size_t)n, n, d + 5 * (size_t)n, ctx->stream);
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpy(out4, d + 5 * (size_t)n, sizeof(float) * 4 * n, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(ctx, LT_ERR_CUDA, std::string("lt_debug_hemisphere: ") + cudaGetErrorString(e));
   return LT_OK;
 }
 

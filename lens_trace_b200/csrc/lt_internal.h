@@ -89,6 +89,7 @@ struct LtLaunch {
   int accumMode;
   float accumWeight;
   int flags;
+  int refillThreshold;  // k_path: leave the traversal loop when fewer lanes than this still have a ray
   RefCamera cam;
 };
 
@@ -106,3 +107,6 @@ int lt_launch_render(const LtSceneDev& sc, const LtLaunch& L, float* dOut, LtCou
                      cudaStream_t stream);
 int lt_launch_primary_hits(const LtSceneDev& sc, const RefCamera& cam, int kernel, int width, int height,
                            int* dIds, int* dHit, float* dTuv, cudaStream_t stream);
+int lt_launch_debug_random(const float* fx, const float* fy, const float* seed, int n, float* out, cudaStream_t stream);
+int lt_launch_debug_hemisphere(const float* u1, const float* u2, const float* up, int n, float* out,
+                               cudaStream_t stream);

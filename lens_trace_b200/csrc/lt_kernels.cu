@@ -99,86 +99,141 @@ __device__ __forceinline__ bool tri_test(const LtTri* __restrict__ tris, int pri
   return false;
 }
 
-// intersect / intersectIgnorePrimitiveIndex (basic.cu:156-243) on the child-pair layout.
-// Visits children near-first by the sign of the ray direction on the split axis and defers the far
-// child, so triangles are tested in exactly the reference's order; a child whose box is missed is
-// never pushed.  anyHit = stop at the first accepted triangle: exact for shadow rays because the
-// callers read only hitType (basic_lighting.cl:272, global_illumination.cl:296,352).
-// h must be initialised by the caller ({tInit,0,0,0,0}); ignore < 0 = none.
+// The same test for rays whose origin and direction reciprocals are all finite (every ray but the
+// axis-parallel ones).  Without NaNs the select chain above is an interval test:
+// hit <=> max(lo) <= min(hi) && min(hi) > 0, and (bound-o)*inv is monotonic in the bound, so the
+// dirIsNeg-selected lo/hi are min/max of the two products.  Same FSUB/FMUL, so same decisions.
+__device__ __forceinline__ bool slab_fast(float mnx, float mxx, float mny, float mxy, float mnz, float mxz,
+                                          const Ray& r, float ix, float iy, float iz) {
+  float ax = FMUL(FSUB(mnx, r.ox), ix), bx = FMUL(FSUB(mxx, r.ox), ix);
+  float ay = FMUL(FSUB(mny, r.oy), iy), by = FMUL(FSUB(mxy, r.oy), iy);
+  float az = FMUL(FSUB(mnz, r.oz), iz), bz = FMUL(FSUB(mxz, r.oz), iz);
+  float lo = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
+  float hi = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+  return lo <= hi && hi > 0.0f;
+}
+
+// intersect / intersectIgnorePrimitiveIndex (basic.cu:156-243) on the child-pair layout, as a
+// resumable state machine.  Visits children near-first by the sign of the ray direction on the
+// split axis and defers the far child, so triangles are tested in exactly the reference's order; a
+// child whose box is missed is never pushed.  anyHit = stop at the first accepted triangle: exact
+// for shadow rays because the callers read only hitType (basic_lighting.cl:272,
+// global_illumination.cl:296,352).
+#define LT_EXACT_SLAB 8u  // negMask bit: ray has a non-finite reciprocal/origin -> select-chain slab test
+
+struct Trav {
+  Ray r;
+  float ix, iy, iz;
+  unsigned negMask;  // bit k: direction reciprocal on axis k is negative; LT_EXACT_SLAB
+  int cur;           // >= 0 wide node, < 0 leaf (~primitive), LT_DONE finished
+  int sp;
+  int ignore;        // intersectIgnorePrimitiveIndex's primitive, < 0 = none
+  bool anyHit;
+  Hit h;
+};
+
+__device__ __forceinline__ bool finite3(float a, float b, float c) {
+  return fabsf(a) <= FLT_MAX && fabsf(b) <= FLT_MAX && fabsf(c) <= FLT_MAX;
+}
+
+__device__ __forceinline__ bool box_test(const Trav& t, float mnx, float mxx, float mny, float mxy, float mnz,
+                                         float mxz) {
+  if (t.negMask & LT_EXACT_SLAB) {
+    bool nx = t.negMask & 1u, ny = t.negMask & 2u, nz = t.negMask & 4u;
+    return slab(nx ? mxx : mnx, nx ? mnx : mxx, ny ? mxy : mny, ny ? mny : mxy, nz ? mxz : mnz, nz ? mnz : mxz, t.r,
+                t.ix, t.iy, t.iz);
+  }
+  return slab_fast(mnx, mxx, mny, mxy, mnz, mxz, t.r, t.ix, t.iy, t.iz);
+}
+
 template <bool STATS>
-__device__ __forceinline__ void trace(const LtSceneDev& sc, const Ray& r, int ignore, float epsThr, bool anyHit,
-                                      Hit& h, int* __restrict__ stk, LtCounters& cnt) {
-  float ix = FRCP(r.dx), iy = FRCP(r.dy), iz = FRCP(r.dz);
-  bool nx = ix < 0.0f, ny = iy < 0.0f, nz = iz < 0.0f;
-  unsigned negMask = (nx ? 1u : 0u) | (ny ? 2u : 0u) | (nz ? 4u : 0u);
+__device__ __forceinline__ void trav_begin(Trav& t, const LtSceneDev& sc, int ignore, float tInit, bool anyHit,
+                                           LtCounters& cnt) {
+  t.ix = FRCP(t.r.dx);
+  t.iy = FRCP(t.r.dy);
+  t.iz = FRCP(t.r.dz);
+  t.negMask = (t.ix < 0.0f ? 1u : 0u) | (t.iy < 0.0f ? 2u : 0u) | (t.iz < 0.0f ? 4u : 0u);
+  if (!(finite3(t.ix, t.iy, t.iz) && finite3(t.r.ox, t.r.oy, t.r.oz))) t.negMask |= LT_EXACT_SLAB;
+  t.h.t = tInit; t.h.u = 0.0f; t.h.v = 0.0f; t.h.prim = 0; t.h.hit = 0;
+  t.ignore = ignore;
+  t.anyHit = STATS ? false : anyHit;
+  t.sp = 0;
   if (STATS) {
     cnt.rays++;
     cnt.nodeTests++;
-    anyHit = false;
   }
   // root box (reference node 0)
-  {
-    float lox = nx ? sc.rootMax[0] : sc.rootMin[0], hix = nx ? sc.rootMin[0] : sc.rootMax[0];
-    float loy = ny ? sc.rootMax[1] : sc.rootMin[1], hiy = ny ? sc.rootMin[1] : sc.rootMax[1];
-    float loz = nz ? sc.rootMax[2] : sc.rootMin[2], hiz = nz ? sc.rootMin[2] : sc.rootMax[2];
-    if (!slab(lox, hix, loy, hiy, loz, hiz, r, ix, iy, iz)) return;
+  bool hit = box_test(t, sc.rootMin[0], sc.rootMax[0], sc.rootMin[1], sc.rootMax[1], sc.rootMin[2], sc.rootMax[2]);
+  t.cur = hit ? sc.rootRef : LT_DONE;
+  if (STATS && hit && t.cur < 0 && sc.rootCount > 1 && ~t.cur != ignore) cnt.triTests += (unsigned)(sc.rootCount - 1);
+}
+
+__device__ __forceinline__ int trav_pop(Trav& t, const int* __restrict__ stk) {
+  if (t.sp > 0) {
+    t.sp--;
+    return stk[t.sp * LT_BLOCK];
   }
-  int cur = sc.rootRef;
-  int sp = 0;
-  const int stride = LT_BLOCK;
-  if (STATS && cur < 0 && sc.rootCount > 1 && ~cur != ignore) cnt.triTests += (unsigned)(sc.rootCount - 1);
-  while (true) {
-    while (cur >= 0) {
-      const float4* np = reinterpret_cast<const float4*>(sc.wnodes + cur);
-      float4 bx = __ldg(np), by = __ldg(np + 1), bz = __ldg(np + 2);
-      int4 m = __ldg(reinterpret_cast<const int4*>(np) + 3);
-      bool hl = slab(nx ? bx.y : bx.x, nx ? bx.x : bx.y, ny ? by.y : by.x, ny ? by.x : by.y, nz ? bz.y : bz.x,
-                     nz ? bz.x : bz.y, r, ix, iy, iz);
-      bool hr = slab(nx ? bx.w : bx.z, nx ? bx.z : bx.w, ny ? by.w : by.z, ny ? by.z : by.w, nz ? bz.w : bz.z,
-                     nz ? bz.z : bz.w, r, ix, iy, iz);
-      if (STATS) {
-        cnt.nodeTests += 2;
-        // a leaf with primitiveCount n is tested n times by the reference (always the same triangle)
-        unsigned lc = (unsigned)m.w & 0xffffu, rc = (unsigned)m.w >> 16;
-        if (hl && m.x < 0 && lc > 1 && ~m.x != ignore) cnt.triTests += lc - 1;
-        if (hr && m.y < 0 && rc > 1 && ~m.y != ignore) cnt.triTests += rc - 1;
-      }
-      bool axisNeg = (negMask >> m.z) & 1u;
-      int nearRef = axisNeg ? m.y : m.x, farRef = axisNeg ? m.x : m.y;
-      bool hn = axisNeg ? hr : hl, hf = axisNeg ? hl : hr;
-      if (hn) {
-        cur = nearRef;
-        if (hf) {
-          stk[sp * stride] = farRef;
-          sp++;
-        }
-      } else if (hf) {
-        cur = farRef;
-      } else if (sp > 0) {
-        sp--;
-        cur = stk[sp * stride];
-      } else {
-        cur = LT_DONE;
+  return LT_DONE;
+}
+
+// one inner-node step; requires t.cur >= 0
+template <bool STATS>
+__device__ __forceinline__ void trav_node_step(Trav& t, const LtSceneDev& sc, int* __restrict__ stk, LtCounters& cnt) {
+  const float4* np = reinterpret_cast<const float4*>(sc.wnodes + t.cur);
+  float4 bx = __ldg(np), by = __ldg(np + 1), bz = __ldg(np + 2);
+  int4 m = __ldg(reinterpret_cast<const int4*>(np) + 3);
+  bool hl = box_test(t, bx.x, bx.y, by.x, by.y, bz.x, bz.y);
+  bool hr = box_test(t, bx.z, bx.w, by.z, by.w, bz.z, bz.w);
+  if (STATS) {
+    cnt.nodeTests += 2;
+    // a leaf with primitiveCount n is tested n times by the reference (always the same triangle)
+    unsigned lc = (unsigned)m.w & 0xffffu, rc = (unsigned)m.w >> 16;
+    if (hl && m.x < 0 && lc > 1 && ~m.x != t.ignore) cnt.triTests += lc - 1;
+    if (hr && m.y < 0 && rc > 1 && ~m.y != t.ignore) cnt.triTests += rc - 1;
+  }
+  bool axisNeg = (t.negMask >> m.z) & 1u;
+  int nearRef = axisNeg ? m.y : m.x, farRef = axisNeg ? m.x : m.y;
+  bool hn = axisNeg ? hr : hl, hf = axisNeg ? hl : hr;
+  if (hn) {
+    t.cur = nearRef;
+    if (hf) {
+      stk[t.sp * LT_BLOCK] = farRef;
+      t.sp++;
+    }
+  } else if (hf) {
+    t.cur = farRef;
+  } else {
+    t.cur = trav_pop(t, stk);
+  }
+}
+
+// one leaf step; requires t.cur < 0 && t.cur != LT_DONE
+template <bool STATS>
+__device__ __forceinline__ void trav_leaf_step(Trav& t, const LtSceneDev& sc, int* __restrict__ stk, float epsThr,
+                                               LtCounters& cnt) {
+  int prim = ~t.cur;
+  if (prim != t.ignore) {
+    if (STATS) cnt.triTests++;
+    if (tri_test(sc.tris, prim, t.r, epsThr, t.h)) {
+      t.h.prim = prim;
+      t.h.hit = 1;
+      if (t.anyHit) {
+        t.cur = LT_DONE;
+        return;
       }
     }
-    while (cur < 0 && cur != LT_DONE) {
-      int prim = ~cur;
-      if (prim != ignore) {
-        if (STATS) cnt.triTests++;
-        if (tri_test(sc.tris, prim, r, epsThr, h)) {
-          h.prim = prim;
-          h.hit = 1;
-          if (anyHit) return;
-        }
-      }
-      if (sp > 0) {
-        sp--;
-        cur = stk[sp * stride];
-      } else {
-        cur = LT_DONE;
-      }
-    }
-    if (cur == LT_DONE) return;
+  }
+  t.cur = trav_pop(t, stk);
+}
+
+// run one ray to completion (deterministic kernels, hit-record kernel)
+template <bool STATS>
+__device__ __forceinline__ void trace(Trav& t, const LtSceneDev& sc, int ignore, float tInit, float epsThr,
+                                      bool anyHit, int* __restrict__ stk, LtCounters& cnt) {
+  trav_begin<STATS>(t, sc, ignore, tInit, anyHit, cnt);
+  while (t.cur != LT_DONE) {
+    while (t.cur >= 0) trav_node_step<STATS>(t, sc, stk, cnt);
+    while (t.cur < 0 && t.cur != LT_DONE) trav_leaf_step<STATS>(t, sc, stk, epsThr, cnt);
   }
 }
 
@@ -280,49 +335,48 @@ __device__ __forceinline__ void lerp_fused(const float* a, const float* b, const
 }
 
 // traceRayThroughLens + refract, basic.cu:79-86,245-298 (operation order: oracle/notes_fma_order.md)
+// On entry t holds the primary ray and its hit; on exit the refracted ray and its hit.
 template <bool STATS>
-__device__ void lens_path(const LtSceneDev& sc, Ray& ray, Hit& h, float tInit, float epsThr, int* stk,
-                          LtCounters& cnt) {
-  const RefPrim* prim = sc.prims + h.prim;
+__device__ void lens_path(const LtSceneDev& sc, Trav& t, float tInit, float epsThr, int* stk, LtCounters& cnt) {
+  const RefPrim* prim = sc.prims + t.h.prim;
   const RefMaterial* mat = sc.mats + prim->materialIndex;
-  float w0 = bary0(h.u, h.v);
+  int firstPrim = t.h.prim;
+  float w0 = bary0(t.h.u, t.h.v);
   float pos[3], nrm[3];
-  lerp_fused(prim->a, prim->b, prim->c, w0, h.u, h.v, pos);
-  lerp_fused(prim->na, prim->nb, prim->nc, w0, h.u, h.v, nrm);
+  lerp_fused(prim->a, prim->b, prim->c, w0, t.h.u, t.h.v, pos);
+  lerp_fused(prim->na, prim->nb, prim->nc, w0, t.h.u, t.h.v, nrm);
 
   float n = FRCP(mat->ior);
-  float c = dot3z(ray.dx, ray.dy, ray.dz, nrm[0], nrm[1], nrm[2]);
+  float c = dot3z(t.r.dx, t.r.dy, t.r.dz, nrm[0], nrm[1], nrm[2]);
   float sinT2 = (float)__dmul_rn(__dsub_rn(1.0, (double)FMUL(c, c)), (double)FMUL(n, n));
   float cosT = (float)__dsqrt_rn(__dsub_rn(1.0, (double)sinT2));
   float k = FFMA(c, -n, -cosT);
-  Ray r2;
-  r2.ox = pos[0]; r2.oy = pos[1]; r2.oz = pos[2];
-  r2.dx = FFMA(ray.dx, n, FMUL(nrm[0], k));
-  r2.dy = FFMA(ray.dy, n, FMUL(nrm[1], k));
-  r2.dz = FFMA(ray.dz, n, FMUL(nrm[2], k));
+  float dx = FFMA(t.r.dx, n, FMUL(nrm[0], k));
+  float dy = FFMA(t.r.dy, n, FMUL(nrm[1], k));
+  float dz = FFMA(t.r.dz, n, FMUL(nrm[2], k));
   float r2w = FFMA(n, 0.0f, FMUL(k, 0.0f));
+  t.r.ox = pos[0]; t.r.oy = pos[1]; t.r.oz = pos[2];
+  t.r.dx = dx; t.r.dy = dy; t.r.dz = dz;
+  trace<STATS>(t, sc, firstPrim, tInit, epsThr, false, stk, cnt);
 
-  Hit h2 = {tInit, 0.0f, 0.0f, 0, 0};
-  trace<STATS>(sc, r2, h.prim, epsThr, false, h2, stk, cnt);
-
-  prim = sc.prims + h2.prim;
+  int secondPrim = t.h.prim;
+  prim = sc.prims + secondPrim;
   mat = sc.mats + prim->materialIndex;
-  w0 = bary0(h2.u, h2.v);
-  lerp_fused(prim->a, prim->b, prim->c, w0, h2.u, h2.v, pos);
-  lerp_fused(prim->na, prim->nb, prim->nc, w0, h2.u, h2.v, nrm);
+  w0 = bary0(t.h.u, t.h.v);
+  lerp_fused(prim->a, prim->b, prim->c, w0, t.h.u, t.h.v, pos);
+  lerp_fused(prim->na, prim->nb, prim->nc, w0, t.h.u, t.h.v, nrm);
 
   float ior = mat->ior;
-  float c2 = FFMA(0.0f, r2w, FFMA(-r2.dz, nrm[2], FFMA(r2.dx, -nrm[0], -FMUL(r2.dy, nrm[1]))));
+  float c2 = FFMA(0.0f, r2w, FFMA(-t.r.dz, nrm[2], FFMA(t.r.dx, -nrm[0], -FMUL(t.r.dy, nrm[1]))));
   float sinT2b = (float)__dmul_rn(__dsub_rn(1.0, (double)FMUL(c2, c2)), (double)FMUL(ior, ior));
   float cosTb = (float)__dsqrt_rn(__dsub_rn(1.0, (double)sinT2b));
   float k2 = FFMA(c2, -ior, -cosTb);
-
-  ray.ox = pos[0]; ray.oy = pos[1]; ray.oz = pos[2];
-  ray.dx = FFMA(r2.dx, ior, -FMUL(k2, nrm[0]));
-  ray.dy = FFMA(r2.dy, ior, -FMUL(k2, nrm[1]));
-  ray.dz = FFMA(r2.dz, ior, -FMUL(k2, nrm[2]));
-  h.t = tInit; h.u = 0.0f; h.v = 0.0f; h.prim = 0; h.hit = 0;
-  trace<STATS>(sc, ray, h2.prim, epsThr, false, h, stk, cnt);
+  dx = FFMA(t.r.dx, ior, -FMUL(k2, nrm[0]));
+  dy = FFMA(t.r.dy, ior, -FMUL(k2, nrm[1]));
+  dz = FFMA(t.r.dz, ior, -FMUL(k2, nrm[2]));
+  t.r.ox = pos[0]; t.r.oy = pos[1]; t.r.oz = pos[2];
+  t.r.dx = dx; t.r.dy = dy; t.r.dz = dz;
+  trace<STATS>(t, sc, secondPrim, tInit, epsThr, false, stk, cnt);
 }
 
 template <bool STATS>
@@ -334,21 +388,21 @@ __global__ void __launch_bounds__(LT_BLOCK) k_flat(LtSceneDev sc, LtLaunch L, fl
   if (!thread_pixel(L.width, L.height, px, py)) return;
   LtCounters cnt = {0, 0, 0};
   float fx, fy;
-  Ray ray = camera_ray(L.cam, px, py, L.width, L.height, fx, fy);
+  Trav t;
+  t.r = camera_ray(L.cam, px, py, L.width, L.height, fx, fy);
   const float tInit = lt_tinit(L.kernel), epsThr = lt_eps(L.kernel);
   float color[3] = {0.0f, 0.0f, 0.0f};
-  Hit h = {tInit, 0.0f, 0.0f, 0, 0};
-  trace<STATS>(sc, ray, -1, epsThr, false, h, stk, cnt);
-  if (h.hit == 1) {
+  trace<STATS>(t, sc, -1, tInit, epsThr, false, stk, cnt);
+  if (t.h.hit == 1) {
     if (L.kernel == 2) {  // custom_opencl.cl:240
-      color[0] = h.u;
-      color[1] = h.v;
-      color[2] = bary0(h.u, h.v);
+      color[0] = t.h.u;
+      color[1] = t.h.v;
+      color[2] = bary0(t.h.u, t.h.v);
     } else {  // basic.cu:312-326
-      const RefMaterial* mat = sc.mats + sc.prims[h.prim].materialIndex;
+      const RefMaterial* mat = sc.mats + sc.prims[t.h.prim].materialIndex;
       if (mat->dissolve < 1.0f) {
-        lens_path<STATS>(sc, ray, h, tInit, epsThr, stk, cnt);
-        if (h.hit == 1) mat = sc.mats + sc.prims[h.prim].materialIndex;
+        lens_path<STATS>(sc, t, tInit, epsThr, stk, cnt);
+        if (t.h.hit == 1) mat = sc.mats + sc.prims[t.h.prim].materialIndex;
       }
       color[0] = mat->diffuse[0];
       color[1] = mat->diffuse[1];
@@ -415,14 +469,15 @@ __device__ __forceinline__ bool is_light(const LtSceneDev& sc, int prim) {
   return hit;
 }
 
-// light sample: basic_lighting.cl:246-262.  Produces the shadow ray; returns its initial t.
-__device__ __forceinline__ float make_shadow_ray(const LtSceneDev& sc, const float pos[3], float fx, float fy,
-                                                 unsigned seedBase, Ray& sr, float toLight[3]) {
-  int idx = (int)FMUL(lt_random(fx, fy, (float)seedBase), (float)sc.lights->count);
+// light sample: basic_lighting.cl:246-262 with the three random numbers already drawn
+// (rIdx = random(seed), rU = random(seed+1), rV = random(seed+2)).  Overwrites r with the shadow
+// ray (origin = pos, direction = normalize(L - P)) and returns its initial t.
+__device__ __forceinline__ float make_shadow_ray(const LtSceneDev& sc, const float pos[3], float rIdx, float rU,
+                                                 float rV, Ray& sr) {
+  int idx = (int)FMUL(rIdx, (float)sc.lights->count);
   idx = max(0, min(idx, 63));
   const RefPrim* lp = sc.prims + sc.lights->primitives[idx];
-  float ux = lt_random(fx, fy, (float)(seedBase + 1u));
-  float uy = lt_random(fx, fy, (float)(seedBase + 2u));
+  float ux = rU, uy = rV;
   if (FADD(ux, uy) > 1.0f) {
     ux = FSUB(1.0f, ux);
     uy = FSUB(1.0f, uy);
@@ -432,11 +487,10 @@ __device__ __forceinline__ float make_shadow_ray(const LtSceneDev& sc, const flo
   lerp_plain(lp->a, lp->b, lp->c, w0, ux, uy, Lp);
   float dx = FSUB(Lp[0], pos[0]), dy = FSUB(Lp[1], pos[1]), dz = FSUB(Lp[2], pos[2]);
   float len = len3(dx, dy, dz);
-  toLight[0] = FDIV(dx, len);
-  toLight[1] = FDIV(dy, len);
-  toLight[2] = FDIV(dz, len);
   sr.ox = pos[0]; sr.oy = pos[1]; sr.oz = pos[2];
-  sr.dx = toLight[0]; sr.dy = toLight[1]; sr.dz = toLight[2];
+  sr.dx = FDIV(dx, len);
+  sr.dy = FDIV(dy, len);
+  sr.dz = FDIV(dz, len);
   return (float)__dsub_rn((double)len, 0.01);
 }
 
@@ -467,16 +521,22 @@ __device__ __forceinline__ void sample_hemisphere(float u1, float u2, const floa
 
 enum PathStage { ST_PRIMARY = 0, ST_SHADOW_DIRECT = 1, ST_EXTENSION = 2, ST_SHADOW_EXT = 3 };
 
-// One thread = one pixel.  The loop body traces exactly one ray per iteration; what the ray is
-// (primary / shadow / extension) is per-lane state, so lanes at different path depths and
-// different samples still execute the traversal together.
+
+// One thread = one pixel, persistent over all frames and samples of the launch.  The warp alternates
+// between two phases:
+//   S (shade/regenerate): lanes whose ray has finished consume the hit and produce their next ray
+//     (primary, shadow or extension); the hash-RNG draws, the expensive part, are one shared code
+//     site whatever the path stage;
+//   T (traverse): all lanes with an unfinished ray run the while-while traversal; the loop is left
+//     as soon as fewer than L.refillThreshold lanes are still traversing and some lane is waiting
+//     for a new ray, so long rays never hold the other 31 lanes idle.  Traversal state is resumable.
 template <bool STATS>
 __global__ void __launch_bounds__(LT_BLOCK) k_path(LtSceneDev sc, LtLaunch L, float* __restrict__ out,
                                                    LtCounters* gcnt) {
   extern __shared__ int smemStack[];
   int* stk = smemStack + threadIdx.x;
   int px, py;
-  if (!thread_pixel(L.width, L.height, px, py)) return;
+  bool alive = thread_pixel(L.width, L.height, px, py);
   LtCounters cnt = {0, 0, 0};
 
   const float tInit = lt_tinit(L.kernel), epsThr = lt_eps(L.kernel);
@@ -485,168 +545,192 @@ __global__ void __launch_bounds__(LT_BLOCK) k_path(LtSceneDev sc, LtLaunch L, fl
   const int samplesPerFrame = (L.kernel == 3 || L.kernel == 5) ? 25 : 1;
   const int maxDepth = L.maxRayDepth > 0 ? L.maxRayDepth : 16;
 
-  float fx, fy;
-  const Ray cameraRay = camera_ray(L.cam, px, py, L.width, L.height, fx, fy);
-  long long id = ((long long)py * L.width + px) * L.depth;
+  float fx = 0.0f, fy = 0.0f;
+  Ray cameraRay = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 1.0f};
+  long long id = 0;
   FrameSink sink;
-  sink.begin(L, out, id);
+  sink.acc[0] = sink.acc[1] = sink.acc[2] = 0.0f;
+  if (alive) {
+    cameraRay = camera_ray(L.cam, px, py, L.width, L.height, fx, fy);
+    id = ((long long)py * L.width + px) * L.depth;
+    sink.begin(L, out, id);
+  }
 
   int frame = 0, sample = 0;
   float frameColor[3] = {0.0f, 0.0f, 0.0f};
+  unsigned sampleIndex = (samplesPerFrame == 25) ? L.cam.frameCount * 32u : L.cam.frameCount;
 
   // per-sample state
   int stage = ST_PRIMARY;
-  Ray ray = cameraRay;
-  int ignore = -1;
-  float tStart = tInit;
-  bool anyHit = false;
-  float direct[3], indirect[3];
-  float pos[3], nrm[3], diffuse[3], toLight[3];
-  float prevN[3], extW = 0.0f;
-  Ray ext;
-  int prevPrim = 0, hitPrim = 0, depth = 0;
-  unsigned sampleIndex = (samplesPerFrame == 25) ? L.cam.frameCount * 32u : L.cam.frameCount;
-  direct[0] = direct[1] = direct[2] = 0.0f;
-  indirect[0] = indirect[1] = indirect[2] = 0.0f;
+  float direct[3] = {0.0f, 0.0f, 0.0f}, indirect[3] = {0.0f, 0.0f, 0.0f};
+  float nrm[3] = {0.0f, 0.0f, 0.0f}, diffuse[3] = {0.0f, 0.0f, 0.0f};
+  float extW = 0.0f;
+  int hitPrim = 0, depth = 0;
 
-  while (frame < L.frames) {
-    Hit h = {tStart, 0.0f, 0.0f, 0, 0};
-    trace<STATS>(sc, ray, ignore, epsThr, anyHit, h, stk, cnt);
+  Trav t;
+  t.r = cameraRay;
+  bool traversing = false;
+  if (alive) {
+    trav_begin<STATS>(t, sc, -1, tInit, false, cnt);
+    traversing = (t.cur != LT_DONE);
+  }
 
-    bool sampleDone = false;
-    bool wantShadow = false;     // next ray: shadow ray from (pos, hitPrim)
-    unsigned shadowSeed = 0;
+  while (true) {
+    // ---------------- phase S: consume finished rays, generate the next ones ----------------
+    while (alive && !traversing) {
+      const Hit h = t.h;
+      bool sampleDone = false, wantShadow = false, wantExt = false, retrace = false;
+      unsigned seedBase = 0;
 
-    if (stage == ST_PRIMARY) {
-      // basic_lighting.cl:230-246 / accumulator.cl:233-238 / global_illumination.cl:255-274
-      bool lightHit = (isGI || whiteOnLight) && is_light(sc, h.prim);
-      if (lightHit) {
-        direct[0] = direct[1] = direct[2] = 1.0f;
-        sampleDone = true;
-      } else if (h.hit == 1) {
-        const RefPrim* prim = sc.prims + h.prim;
-        const RefMaterial* mat = sc.mats + prim->materialIndex;
-        float w0 = bary0(h.u, h.v);
-        lerp_plain(prim->a, prim->b, prim->c, w0, h.u, h.v, pos);
-        lerp_plain(prim->na, prim->nb, prim->nc, w0, h.u, h.v, nrm);
-        diffuse[0] = mat->diffuse[0]; diffuse[1] = mat->diffuse[1]; diffuse[2] = mat->diffuse[2];
-        hitPrim = h.prim;
-        wantShadow = true;
-        shadowSeed = sampleIndex;
-        stage = ST_SHADOW_DIRECT;
-      } else {
-        sampleDone = true;
-      }
-    } else if (stage == ST_SHADOW_DIRECT) {
-      if (h.hit == 0) {  // basic_lighting.cl:272-274
-        float d = dot3plain(toLight, nrm);
-        direct[0] = FMUL(diffuse[0], d); direct[1] = FMUL(diffuse[1], d); direct[2] = FMUL(diffuse[2], d);
-      }
-      if (isGI && maxDepth > 0) {  // global_illumination.cl:300-309
-        float dir[4];
-        sample_hemisphere(lt_random(fx, fy, (float)(sampleIndex + 3u)), lt_random(fx, fy, (float)(sampleIndex + 4u)),
-                          nrm, dir);
-        ext.ox = pos[0]; ext.oy = pos[1]; ext.oz = pos[2];
-        ext.dx = dir[0]; ext.dy = dir[1]; ext.dz = dir[2];
-        extW = dir[3];
-        prevN[0] = nrm[0]; prevN[1] = nrm[1]; prevN[2] = nrm[2];
-        prevPrim = hitPrim;
-        depth = 0;
-        stage = ST_EXTENSION;
-      } else {
-        sampleDone = true;
-      }
-    } else if (stage == ST_EXTENSION) {
-      // global_illumination.cl:310-370
-      float w = (float)__ddiv_rn(1.0, (double)(depth + 1));
-      if (is_light(sc, h.prim)) {
-        float d = FADD(FADD(FADD(FMUL(prevN[0], ext.dx), FMUL(prevN[1], ext.dy)), FMUL(prevN[2], ext.dz)),
-                       FMUL(1.0f, extW));
-        float c = FMUL(FMUL(w, 1.0f), d);
-        indirect[0] = FADD(indirect[0], c); indirect[1] = FADD(indirect[1], c); indirect[2] = FADD(indirect[2], c);
-        depth++;  // ray not advanced: the same hit is found again at the next depth (:320-322)
-        if (depth >= maxDepth) sampleDone = true;
-      } else if (h.hit == 1) {
-        const RefPrim* prim = sc.prims + h.prim;
-        const RefMaterial* mat = sc.mats + prim->materialIndex;
-        float w0 = bary0(h.u, h.v);
-        lerp_plain(prim->a, prim->b, prim->c, w0, h.u, h.v, pos);
-        lerp_plain(prim->na, prim->nb, prim->nc, w0, h.u, h.v, nrm);
-        diffuse[0] = mat->diffuse[0]; diffuse[1] = mat->diffuse[1]; diffuse[2] = mat->diffuse[2];
-        hitPrim = h.prim;
-        wantShadow = true;
-        shadowSeed = sampleIndex + (unsigned)depth + 5u;
-        stage = ST_SHADOW_EXT;
-      } else {
-        sampleDone = true;
-      }
-    } else {  // ST_SHADOW_EXT, global_illumination.cl:352-365
-      if (h.hit == 0) {
-        float w = (float)__ddiv_rn(1.0, (double)(depth + 1));
-        float d = dot3plain(toLight, nrm);
-        indirect[0] = FADD(indirect[0], FMUL(FMUL(w, diffuse[0]), d));
-        indirect[1] = FADD(indirect[1], FMUL(FMUL(w, diffuse[1]), d));
-        indirect[2] = FADD(indirect[2], FMUL(FMUL(w, diffuse[2]), d));
-        float dir[4];
-        sample_hemisphere(lt_random(fx, fy, (float)(sampleIndex + (unsigned)depth + 8u)),
-                          lt_random(fx, fy, (float)(sampleIndex + (unsigned)depth + 9u)), nrm, dir);
-        ext.ox = pos[0]; ext.oy = pos[1]; ext.oz = pos[2];
-        ext.dx = dir[0]; ext.dy = dir[1]; ext.dz = dir[2];
-        extW = dir[3];
-        prevN[0] = nrm[0]; prevN[1] = nrm[1]; prevN[2] = nrm[2];
-        prevPrim = hitPrim;
-        depth++;
-        stage = ST_EXTENSION;
-        if (depth >= maxDepth) sampleDone = true;
-      } else {
-        sampleDone = true;
-      }
-    }
-
-    if (sampleDone) {
-      float c[3] = {FADD(direct[0], indirect[0]), FADD(direct[1], indirect[1]), FADD(direct[2], indirect[2])};
-      if (samplesPerFrame == 1) {
-        frameColor[0] = c[0]; frameColor[1] = c[1]; frameColor[2] = c[2];
-      } else if (sample == 0) {
-        frameColor[0] = c[0]; frameColor[1] = c[1]; frameColor[2] = c[2];
-      } else {  // basic_lighting.cl:310-316: recency-weighted blend
-        float a = FDIV((float)(25 - sample), 25.0f);
-        float ia = FSUB(1.0f, a);
-#pragma unroll
-        for (int k = 0; k < 3; k++) frameColor[k] = FADD(FMUL(ia, frameColor[k]), FMUL(a, c[k]));
-      }
-      sample++;
-      if (sample == samplesPerFrame) {
-        if (samplesPerFrame == 25 && L.kernelMode == 0) {  // clamp only in linearKernel (:318-320)
-#pragma unroll
-          for (int k = 0; k < 3; k++) frameColor[k] = fminf(fmaxf(frameColor[k], 0.0f), 1.0f);
+      if (stage == ST_PRIMARY || stage == ST_EXTENSION) {
+        // basic_lighting.cl:230-246 / accumulator.cl:233-238 / global_illumination.cl:255-274, 310-331
+        bool lightHit = (stage == ST_EXTENSION || isGI || whiteOnLight) && is_light(sc, h.prim);
+        if (lightHit) {
+          if (stage == ST_PRIMARY) {
+            direct[0] = direct[1] = direct[2] = 1.0f;
+            sampleDone = true;
+          } else {
+            // dot(previousNormal (w = 1), direction (w = hemisphere.y)), global_illumination.cl:321;
+            // the ray is not advanced, so the same hit is found again at the next depth
+            float w = (float)__ddiv_rn(1.0, (double)(depth + 1));
+            float d = FADD(FADD(FADD(FMUL(nrm[0], t.r.dx), FMUL(nrm[1], t.r.dy)), FMUL(nrm[2], t.r.dz)),
+                           FMUL(1.0f, extW));
+            float c = FMUL(FMUL(w, 1.0f), d);
+            indirect[0] = FADD(indirect[0], c); indirect[1] = FADD(indirect[1], c); indirect[2] = FADD(indirect[2], c);
+            depth++;
+            if (depth >= maxDepth) sampleDone = true;
+            else retrace = true;
+          }
+        } else if (h.hit == 1) {
+          const RefPrim* prim = sc.prims + h.prim;
+          const RefMaterial* mat = sc.mats + prim->materialIndex;
+          float w0 = bary0(h.u, h.v);
+          float pos[3];
+          lerp_plain(prim->a, prim->b, prim->c, w0, h.u, h.v, pos);
+          lerp_plain(prim->na, prim->nb, prim->nc, w0, h.u, h.v, nrm);
+          diffuse[0] = mat->diffuse[0]; diffuse[1] = mat->diffuse[1]; diffuse[2] = mat->diffuse[2];
+          hitPrim = h.prim;
+          t.r.ox = pos[0]; t.r.oy = pos[1]; t.r.oz = pos[2];  // origin of the shadow ray and of the next extension
+          wantShadow = true;
+          seedBase = (stage == ST_PRIMARY) ? sampleIndex : sampleIndex + (unsigned)depth + 5u;
+          stage = (stage == ST_PRIMARY) ? ST_SHADOW_DIRECT : ST_SHADOW_EXT;
+        } else {
+          sampleDone = true;
         }
-        unsigned fc = L.cam.frameCount + (unsigned)frame * L.frameStride;
-        sink.frame(L, fc, frameColor);
-        sample = 0;
-        frame++;
+      } else {
+        // the shadow ray's direction is positionToLight, its origin the shaded position
+        bool lit = (h.hit == 0);
+        float d = FADD(FADD(FMUL(t.r.dx, nrm[0]), FMUL(t.r.dy, nrm[1])), FMUL(t.r.dz, nrm[2]));
+        if (stage == ST_SHADOW_DIRECT) {  // basic_lighting.cl:272-274, global_illumination.cl:296-309
+          if (lit) {
+            direct[0] = FMUL(diffuse[0], d); direct[1] = FMUL(diffuse[1], d); direct[2] = FMUL(diffuse[2], d);
+          }
+          if (isGI && maxDepth > 0) {
+            wantExt = true;
+            seedBase = sampleIndex + 3u;
+            depth = 0;
+          } else {
+            sampleDone = true;
+          }
+        } else {  // global_illumination.cl:352-365
+          if (lit) {
+            float w = (float)__ddiv_rn(1.0, (double)(depth + 1));
+            indirect[0] = FADD(indirect[0], FMUL(FMUL(w, diffuse[0]), d));
+            indirect[1] = FADD(indirect[1], FMUL(FMUL(w, diffuse[1]), d));
+            indirect[2] = FADD(indirect[2], FMUL(FMUL(w, diffuse[2]), d));
+            seedBase = sampleIndex + (unsigned)depth + 8u;
+            depth++;
+            // the reference still draws a direction at the last depth, but never traces it
+            if (depth >= maxDepth) sampleDone = true;
+            else wantExt = true;
+          } else {
+            sampleDone = true;
+          }
+        }
       }
-      unsigned fcNext = L.cam.frameCount + (unsigned)frame * L.frameStride;
-      sampleIndex = (samplesPerFrame == 25) ? fcNext * 32u + (unsigned)sample : fcNext;
-      direct[0] = direct[1] = direct[2] = 0.0f;
-      indirect[0] = indirect[1] = indirect[2] = 0.0f;
-      stage = ST_PRIMARY;
-      ray = cameraRay;
-      ignore = -1;
-      tStart = tInit;
-      anyHit = false;
-    } else if (wantShadow) {
-      tStart = make_shadow_ray(sc, pos, fx, fy, shadowSeed, ray, toLight);
-      ignore = hitPrim;
-      anyHit = true;
-    } else {  // extension ray
-      ray = ext;
-      ignore = prevPrim;
-      tStart = tInit;
-      anyHit = false;
+
+      // the hash RNG (fp64 fmod + sin), one code site for every stage
+      float rA = 0.0f, rB = 0.0f, rC = 0.0f;
+      if (wantShadow || wantExt) {
+        rA = lt_random(fx, fy, (float)seedBase);
+        rB = lt_random(fx, fy, (float)(seedBase + 1u));
+        if (wantShadow) rC = lt_random(fx, fy, (float)(seedBase + 2u));
+      }
+
+      int ignore = -1;
+      float tStart = tInit;
+      bool anyHit = false;
+      if (wantShadow) {
+        float pos[3] = {t.r.ox, t.r.oy, t.r.oz};
+        tStart = make_shadow_ray(sc, pos, rA, rB, rC, t.r);
+        ignore = hitPrim;
+        anyHit = true;
+      } else if (wantExt) {  // global_illumination.cl:300-305, 355-361
+        float dir[4];
+        sample_hemisphere(rA, rB, nrm, dir);
+        t.r.dx = dir[0]; t.r.dy = dir[1]; t.r.dz = dir[2];  // origin stays the shaded position
+        extW = dir[3];
+        ignore = hitPrim;
+        stage = ST_EXTENSION;
+      } else if (retrace) {
+        ignore = hitPrim;
+      }
+
+      if (sampleDone) {
+        // GI returns directColor + indirectColor (global_illumination.cl:375); the lighting kernels
+        // return outputColor as is (basic_lighting.cl:277) -- the add would turn -0 into +0
+        float c[3] = {direct[0], direct[1], direct[2]};
+        if (isGI) {
+          c[0] = FADD(direct[0], indirect[0]); c[1] = FADD(direct[1], indirect[1]); c[2] = FADD(direct[2], indirect[2]);
+        }
+        if (samplesPerFrame == 1 || sample == 0) {
+          frameColor[0] = c[0]; frameColor[1] = c[1]; frameColor[2] = c[2];
+        } else {  // basic_lighting.cl:310-316: recency-weighted blend
+          float a = FDIV((float)(25 - sample), 25.0f);
+          float ia = FSUB(1.0f, a);
+#pragma unroll
+          for (int k = 0; k < 3; k++) frameColor[k] = FADD(FMUL(ia, frameColor[k]), FMUL(a, c[k]));
+        }
+        sample++;
+        if (sample == samplesPerFrame) {
+          if (samplesPerFrame == 25 && L.kernelMode == 0) {  // clamp only in linearKernel (:318-320)
+#pragma unroll
+            for (int k = 0; k < 3; k++) frameColor[k] = fminf(fmaxf(frameColor[k], 0.0f), 1.0f);
+          }
+          sink.frame(L, L.cam.frameCount + (unsigned)frame * L.frameStride, frameColor);
+          sample = 0;
+          frame++;
+          if (frame >= L.frames) {
+            sink.end(out, id);
+            alive = false;
+            break;
+          }
+        }
+        unsigned fcNext = L.cam.frameCount + (unsigned)frame * L.frameStride;
+        sampleIndex = (samplesPerFrame == 25) ? fcNext * 32u + (unsigned)sample : fcNext;
+        direct[0] = direct[1] = direct[2] = 0.0f;
+        indirect[0] = indirect[1] = indirect[2] = 0.0f;
+        stage = ST_PRIMARY;
+        t.r = cameraRay;
+      }
+      trav_begin<STATS>(t, sc, ignore, tStart, anyHit, cnt);
+      traversing = (t.cur != LT_DONE);
+    }
+    if (!__any_sync(0xffffffffu, alive)) break;
+
+    // ---------------- phase T: resumable while-while traversal ----------------
+    while (true) {
+      unsigned active = __ballot_sync(0xffffffffu, traversing);
+      if (active == 0u) break;
+      bool waiting = __any_sync(0xffffffffu, alive && !traversing);
+      if (waiting && __popc(active) < L.refillThreshold) break;
+      if (traversing) {
+        while (t.cur >= 0) trav_node_step<STATS>(t, sc, stk, cnt);
+        while (t.cur < 0 && t.cur != LT_DONE) trav_leaf_step<STATS>(t, sc, stk, epsThr, cnt);
+        traversing = (t.cur != LT_DONE);
+      }
     }
   }
-  sink.end(out, id);
   if (STATS) flush_counters(gcnt, cnt);
 }
 
@@ -662,9 +746,10 @@ __global__ void __launch_bounds__(LT_BLOCK) k_primary_hits(LtSceneDev sc, RefCam
   if (!thread_pixel(width, height, px, py)) return;
   LtCounters cnt = {0, 0, 0};
   float fx, fy;
-  Ray ray = camera_ray(cam, px, py, width, height, fx, fy);
-  Hit h = {lt_tinit(kernel), 0.0f, 0.0f, 0, 0};
-  trace<false>(sc, ray, -1, lt_eps(kernel), false, h, stk, cnt);
+  Trav t;
+  t.r = camera_ray(cam, px, py, width, height, fx, fy);
+  trace<false>(t, sc, -1, lt_tinit(kernel), lt_eps(kernel), false, stk, cnt);
+  const Hit h = t.h;
   long long i = (long long)py * width + px;
   if (ids) ids[i] = h.prim;
   if (hit) hit[i] = h.hit;
@@ -673,6 +758,23 @@ __global__ void __launch_bounds__(LT_BLOCK) k_primary_hits(LtSceneDev sc, RefCam
     tuv[3 * i + 1] = h.u;
     tuv[3 * i + 2] = h.v;
   }
+}
+
+// device evaluation of the hash RNG and hemisphere sampler on caller-supplied inputs (parity hook)
+__global__ void k_debug_random(const float* __restrict__ fx, const float* __restrict__ fy, const float* __restrict__ seed,
+                               int n, float* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = lt_random(fx[i], fy[i], seed[i]);
+}
+
+__global__ void k_debug_hemisphere(const float* __restrict__ u1, const float* __restrict__ u2,
+                                   const float* __restrict__ up, int n, float* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float upv[3] = {up[3 * i], up[3 * i + 1], up[3 * i + 2]};
+  float d[4];
+  sample_hemisphere(u1[i], u2[i], upv, d);
+  out[4 * i + 0] = d[0]; out[4 * i + 1] = d[1]; out[4 * i + 2] = d[2]; out[4 * i + 3] = d[3];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -716,6 +818,17 @@ __global__ void k_build_tris(const RefPrim* __restrict__ prims, int n, LtTri* __
 // ------------------------------------------------------------------------------------------------
 // host-side launchers
 // ------------------------------------------------------------------------------------------------
+int lt_launch_debug_random(const float* fx, const float* fy, const float* seed, int n, float* out, cudaStream_t stream) {
+  k_debug_random<<<(n + 255) / 256, 256, 0, stream>>>(fx, fy, seed, n, out);
+  return 1;
+}
+
+int lt_launch_debug_hemisphere(const float* u1, const float* u2, const float* up, int n, float* out,
+                               cudaStream_t stream) {
+  k_debug_hemisphere<<<(n + 255) / 256, 256, 0, stream>>>(u1, u2, up, n, out);
+  return 1;
+}
+
 int lt_launch_inner_flags(const RefNode* dNodes, int nodeCount, int* dFlags, cudaStream_t stream) {
   k_inner_flags<<<(nodeCount + 255) / 256, 256, 0, stream>>>(dNodes, nodeCount, dFlags);
   return 1;

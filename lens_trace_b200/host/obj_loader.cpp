@@ -136,6 +136,85 @@ bool parseCorner(const char*& p, int nv, int nvt, int nvn, Corner* c) {
   return true;
 }
 
+// crossing-number point-in-polygon test on a projected triangle
+bool insideTriangle2D(const float px[3], const float py[3], float tx, float ty) {
+  bool in = false;
+  for (int i = 0, j = 2; i < 3; j = i++) {
+    if (((py[i] > ty) != (py[j] > ty)) && (tx < (px[j] - px[i]) * (ty - py[i]) / (py[j] - py[i]) + px[i])) in = !in;
+  }
+  return in;
+}
+
+// Ear clipping of a polygon with > 4 corners.  Decision sequence (projection axes from the first
+// non-degenerate corner, signed area, candidate ear at a moving cursor, reject reflex corners and
+// ears containing another vertex, bounded retries) mirrors tiny_obj_loader.h:1505-1716.
+template <class Emit>
+void clipEars(const std::vector<Corner>& face, const std::vector<float>& v, Emit emit) {
+  size_t n = face.size();
+  auto valid = [&](int vi) { return vi >= 0 && (size_t)(3 * vi + 2) < v.size(); };
+  size_t ax0 = 1, ax1 = 2;
+  for (size_t k = 0; k < n; k++) {
+    int a = face[k % n].v, b = face[(k + 1) % n].v, c = face[(k + 2) % n].v;
+    if (!valid(a) || !valid(b) || !valid(c)) continue;
+    float e0x = v[3 * b] - v[3 * a], e0y = v[3 * b + 1] - v[3 * a + 1], e0z = v[3 * b + 2] - v[3 * a + 2];
+    float e1x = v[3 * c] - v[3 * b], e1y = v[3 * c + 1] - v[3 * b + 1], e1z = v[3 * c + 2] - v[3 * b + 2];
+    float cx = fabsf(e0y * e1z - e0z * e1y), cy = fabsf(e0z * e1x - e0x * e1z), cz = fabsf(e0x * e1y - e0y * e1x);
+    const float eps = 1.1920929e-07f;
+    if (cx > eps || cy > eps || cz > eps) {
+      if (!(cx > cy && cx > cz)) {
+        ax0 = 0;
+        if (cz > cx && cz > cy) ax1 = 1;
+      }
+      break;
+    }
+  }
+  float area = 0;
+  for (size_t k = 0; k < n; k++) {
+    int a = face[k % n].v, b = face[(k + 1) % n].v;
+    if (!valid(a) || !valid(b)) continue;
+    area += (v[3 * a + ax0] * v[3 * b + ax1] - v[3 * a + ax1] * v[3 * b + ax0]) * 0.5f;
+  }
+  std::vector<int> remaining(n);  // positions into `face`
+  for (size_t k = 0; k < n; k++) remaining[k] = (int)k;
+  size_t cursor = 0, budget = n, previous = n;
+  while (remaining.size() > 3 && budget > 0) {
+    size_t m = remaining.size();
+    if (cursor >= m) cursor -= m;
+    if (previous != m) {
+      previous = m;
+      budget = m;
+    } else {
+      budget--;
+    }
+    int pos[3];
+    float px[3], py[3];
+    for (int k = 0; k < 3; k++) {
+      pos[k] = remaining[(cursor + k) % m];
+      int vi = face[pos[k]].v;
+      px[k] = valid(vi) ? v[3 * vi + ax0] : 0.0f;
+      py[k] = valid(vi) ? v[3 * vi + ax1] : 0.0f;
+    }
+    float cross = (px[1] - px[0]) * (py[2] - py[1]) - (py[1] - py[0]) * (px[2] - px[1]);
+    if (cross * area < 0.0f) {  // reflex corner
+      cursor++;
+      continue;
+    }
+    bool blocked = false;
+    for (size_t o = 3; o < m && !blocked; o++) {
+      int vi = face[remaining[(cursor + o) % m]].v;
+      if (!valid(vi)) continue;
+      blocked = insideTriangle2D(px, py, v[3 * vi + ax0], v[3 * vi + ax1]);
+    }
+    if (blocked) {
+      cursor++;
+      continue;
+    }
+    emit(pos[0], pos[1], pos[2]);
+    remaining.erase(remaining.begin() + (cursor + 1) % m);
+  }
+  if (remaining.size() == 3) emit(remaining[0], remaining[1], remaining[2]);
+}
+
 void initMaterial(material_t* m) {
   m->name.clear();
   for (int i = 0; i < 3; i++) m->ambient[i] = m->diffuse[i] = m->specular[i] = m->transmittance[i] = m->emission[i] = 0.f;
@@ -316,9 +395,10 @@ bool LoadObj(attrib_t* attrib, std::vector<shape_t>* shapes, std::vector<materia
           emit(1, 2, 3);
         }
       } else {
-        // polygons with more than four corners: simple fan (the reference's loader ear-clips;
-        // none of the shipped or generated models contain such faces)
-        for (size_t k = 1; k + 1 < n; k++) emit(0, (int)k, (int)k + 1);
+        // Polygons with more than four corners (cornell_box.obj has an 8-corner ceiling ring):
+        // ear clipping with the same decisions as the loader the reference vendors
+        // (tiny_obj_loader.h:1505-1716), so the triangles -- and primitive numbering -- agree.
+        clipEars(face, v, emit);
       }
     } else if (!strncmp(p, "usemtl", 6) && isSpace(p[6])) {
       p += 7;

@@ -42,6 +42,8 @@ def load():
         lib.lto_accumulate.restype = None
         lib.lto_random.argtypes = [C.c_float] * 3
         lib.lto_random.restype = C.c_float
+        lib.lto_hemisphere.argtypes = [C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+        lib.lto_hemisphere.restype = None
         lib.lto_cuda_cosf.argtypes = [C.c_float]
         lib.lto_cuda_cosf.restype = C.c_float
         lib.lto_cuda_sinf.argtypes = [C.c_float]
@@ -97,3 +99,11 @@ def accumulate(acc, sample, frame_count):
 
 def random(u, v, seed):
     return load().lto_random(u, v, seed)
+
+
+def hemisphere(u1, u2, up):
+    lib = load()
+    upa = np.ascontiguousarray(up, dtype=np.float32)
+    out = np.zeros(4, np.float32)
+    lib.lto_hemisphere(float(u1), float(u2), upa.ctypes.data, out.ctypes.data)
+    return out
