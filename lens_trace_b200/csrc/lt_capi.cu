@@ -276,11 +276,22 @@ static int check_params(lt_ctx* ctx, const lt_scene* scene, const void* camera28
     static int threshold = -1;
     if (threshold < 0) {
       const char* e = getenv("LT_REFILL_THRESHOLD");
-      threshold = e ? atoi(e) : 20;
+      threshold = e ? atoi(e) : 4;
       if (threshold < 1) threshold = 1;
       if (threshold > 32) threshold = 32;
     }
     L->refillThreshold = threshold;
+    static int bAny = -1, bClosest = -1;
+    if (bAny < 0) {
+      const char* e = getenv("LT_BATCH_ANYHIT");
+      bAny = e ? atoi(e) : 16;
+      e = getenv("LT_BATCH_CLOSEST");
+      bClosest = e ? atoi(e) : 16;
+      bAny = bAny < 1 ? 1 : (bAny > 16 ? 16 : bAny);
+      bClosest = bClosest < 1 ? 1 : (bClosest > 16 ? 16 : bClosest);
+    }
+    L->batchAnyHit = bAny;
+    L->batchClosest = bClosest;
   }
   memcpy(&L->cam, camera28, sizeof(RefCamera));
   return LT_OK;

@@ -90,6 +90,8 @@ struct LtLaunch {
   float accumWeight;
   int flags;
   int refillThreshold;  // k_path: leave the traversal loop when fewer lanes than this still have a ray
+  int batchAnyHit;      // k_path: leaves recorded before a shadow ray tests them (early-out granularity)
+  int batchClosest;     // k_path: leaves recorded before a closest-hit ray tests them
   RefCamera cam;
 };
 

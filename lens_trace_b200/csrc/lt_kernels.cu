@@ -207,33 +207,62 @@ __device__ __forceinline__ void trav_node_step(Trav& t, const LtSceneDev& sc, in
   }
 }
 
-// one leaf step; requires t.cur < 0 && t.cur != LT_DONE
+// Traversal never depends on triangle results (the reference does not cull by t, basic.cu:136-154),
+// so box tests and triangle tests are decoupled: the node phase walks the tree and only RECORDS the
+// leaves it reaches, in order, in a small per-thread list in shared memory; the leaf phase then
+// tests the recorded triangles in that order.  A warp therefore switches between "all lanes test
+// boxes" and "all lanes test triangles" once per batch instead of at every leaf.
+#define LT_MAX_BATCH 16  // list entries per thread (shared memory: [LT_MAX_BATCH][LT_BLOCK] ints)
+
+// node phase: advance until the ray is exhausted (t.cur == LT_DONE) or `batch` leaves are recorded.
+// Returns the number of recorded leaves.
 template <bool STATS>
-__device__ __forceinline__ void trav_leaf_step(Trav& t, const LtSceneDev& sc, int* __restrict__ stk, float epsThr,
-                                               LtCounters& cnt) {
-  int prim = ~t.cur;
-  if (prim != t.ignore) {
+__device__ __forceinline__ int trav_collect(Trav& t, const LtSceneDev& sc, int* __restrict__ stk,
+                                            int* __restrict__ list, int batch, LtCounters& cnt) {
+  int n = 0;
+  while (t.cur != LT_DONE && n < batch) {
+    if (t.cur >= 0) {
+      trav_node_step<STATS>(t, sc, stk, cnt);
+    } else {
+      int prim = ~t.cur;
+      if (prim != t.ignore) {
+        list[n * LT_BLOCK] = prim;
+        n++;
+      }
+      t.cur = trav_pop(t, stk);
+    }
+  }
+  return n;
+}
+
+// leaf phase: test the recorded triangles in order.  Returns true if the ray is finished early
+// (any-hit ray that found a hit).
+template <bool STATS>
+__device__ __forceinline__ bool trav_test(Trav& t, const LtSceneDev& sc, const int* __restrict__ list, int n,
+                                          float epsThr, LtCounters& cnt) {
+  for (int i = 0; i < n; i++) {
+    int prim = list[i * LT_BLOCK];
     if (STATS) cnt.triTests++;
     if (tri_test(sc.tris, prim, t.r, epsThr, t.h)) {
       t.h.prim = prim;
       t.h.hit = 1;
       if (t.anyHit) {
         t.cur = LT_DONE;
-        return;
+        return true;
       }
     }
   }
-  t.cur = trav_pop(t, stk);
+  return false;
 }
 
 // run one ray to completion (deterministic kernels, hit-record kernel)
 template <bool STATS>
 __device__ __forceinline__ void trace(Trav& t, const LtSceneDev& sc, int ignore, float tInit, float epsThr,
-                                      bool anyHit, int* __restrict__ stk, LtCounters& cnt) {
+                                      bool anyHit, int* __restrict__ stk, int* __restrict__ list, LtCounters& cnt) {
   trav_begin<STATS>(t, sc, ignore, tInit, anyHit, cnt);
   while (t.cur != LT_DONE) {
-    while (t.cur >= 0) trav_node_step<STATS>(t, sc, stk, cnt);
-    while (t.cur < 0 && t.cur != LT_DONE) trav_leaf_step<STATS>(t, sc, stk, epsThr, cnt);
+    int n = trav_collect<STATS>(t, sc, stk, list, LT_MAX_BATCH, cnt);
+    trav_test<STATS>(t, sc, list, n, epsThr, cnt);
   }
 }
 
@@ -337,7 +366,8 @@ __device__ __forceinline__ void lerp_fused(const float* a, const float* b, const
 // traceRayThroughLens + refract, basic.cu:79-86,245-298 (operation order: oracle/notes_fma_order.md)
 // On entry t holds the primary ray and its hit; on exit the refracted ray and its hit.
 template <bool STATS>
-__device__ void lens_path(const LtSceneDev& sc, Trav& t, float tInit, float epsThr, int* stk, LtCounters& cnt) {
+__device__ void lens_path(const LtSceneDev& sc, Trav& t, float tInit, float epsThr, int* stk, int* list,
+                          LtCounters& cnt) {
   const RefPrim* prim = sc.prims + t.h.prim;
   const RefMaterial* mat = sc.mats + prim->materialIndex;
   int firstPrim = t.h.prim;
@@ -357,7 +387,7 @@ __device__ void lens_path(const LtSceneDev& sc, Trav& t, float tInit, float epsT
   float r2w = FFMA(n, 0.0f, FMUL(k, 0.0f));
   t.r.ox = pos[0]; t.r.oy = pos[1]; t.r.oz = pos[2];
   t.r.dx = dx; t.r.dy = dy; t.r.dz = dz;
-  trace<STATS>(t, sc, firstPrim, tInit, epsThr, false, stk, cnt);
+  trace<STATS>(t, sc, firstPrim, tInit, epsThr, false, stk, list, cnt);
 
   int secondPrim = t.h.prim;
   prim = sc.prims + secondPrim;
@@ -376,7 +406,7 @@ __device__ void lens_path(const LtSceneDev& sc, Trav& t, float tInit, float epsT
   dz = FFMA(t.r.dz, ior, -FMUL(k2, nrm[2]));
   t.r.ox = pos[0]; t.r.oy = pos[1]; t.r.oz = pos[2];
   t.r.dx = dx; t.r.dy = dy; t.r.dz = dz;
-  trace<STATS>(t, sc, secondPrim, tInit, epsThr, false, stk, cnt);
+  trace<STATS>(t, sc, secondPrim, tInit, epsThr, false, stk, list, cnt);
 }
 
 template <bool STATS>
@@ -384,6 +414,7 @@ __global__ void __launch_bounds__(LT_BLOCK) k_flat(LtSceneDev sc, LtLaunch L, fl
                                                    LtCounters* gcnt) {
   extern __shared__ int smemStack[];
   int* stk = smemStack + threadIdx.x;
+  int* list = smemStack + max(sc.stackDepth, 1) * LT_BLOCK + threadIdx.x;
   int px, py;
   if (!thread_pixel(L.width, L.height, px, py)) return;
   LtCounters cnt = {0, 0, 0};
@@ -392,7 +423,7 @@ __global__ void __launch_bounds__(LT_BLOCK) k_flat(LtSceneDev sc, LtLaunch L, fl
   t.r = camera_ray(L.cam, px, py, L.width, L.height, fx, fy);
   const float tInit = lt_tinit(L.kernel), epsThr = lt_eps(L.kernel);
   float color[3] = {0.0f, 0.0f, 0.0f};
-  trace<STATS>(t, sc, -1, tInit, epsThr, false, stk, cnt);
+  trace<STATS>(t, sc, -1, tInit, epsThr, false, stk, list, cnt);
   if (t.h.hit == 1) {
     if (L.kernel == 2) {  // custom_opencl.cl:240
       color[0] = t.h.u;
@@ -401,7 +432,7 @@ __global__ void __launch_bounds__(LT_BLOCK) k_flat(LtSceneDev sc, LtLaunch L, fl
     } else {  // basic.cu:312-326
       const RefMaterial* mat = sc.mats + sc.prims[t.h.prim].materialIndex;
       if (mat->dissolve < 1.0f) {
-        lens_path<STATS>(sc, t, tInit, epsThr, stk, cnt);
+        lens_path<STATS>(sc, t, tInit, epsThr, stk, list, cnt);
         if (t.h.hit == 1) mat = sc.mats + sc.prims[t.h.prim].materialIndex;
       }
       color[0] = mat->diffuse[0];
@@ -535,6 +566,7 @@ __global__ void __launch_bounds__(LT_BLOCK) k_path(LtSceneDev sc, LtLaunch L, fl
                                                    LtCounters* gcnt) {
   extern __shared__ int smemStack[];
   int* stk = smemStack + threadIdx.x;
+  int* list = smemStack + max(sc.stackDepth, 1) * LT_BLOCK + threadIdx.x;
   int px, py;
   bool alive = thread_pixel(L.width, L.height, px, py);
   LtCounters cnt = {0, 0, 0};
@@ -725,8 +757,8 @@ __global__ void __launch_bounds__(LT_BLOCK) k_path(LtSceneDev sc, LtLaunch L, fl
       bool waiting = __any_sync(0xffffffffu, alive && !traversing);
       if (waiting && __popc(active) < L.refillThreshold) break;
       if (traversing) {
-        while (t.cur >= 0) trav_node_step<STATS>(t, sc, stk, cnt);
-        while (t.cur < 0 && t.cur != LT_DONE) trav_leaf_step<STATS>(t, sc, stk, epsThr, cnt);
+        int n = trav_collect<STATS>(t, sc, stk, list, t.anyHit ? L.batchAnyHit : L.batchClosest, cnt);
+        trav_test<STATS>(t, sc, list, n, epsThr, cnt);
         traversing = (t.cur != LT_DONE);
       }
     }
@@ -742,13 +774,14 @@ __global__ void __launch_bounds__(LT_BLOCK) k_primary_hits(LtSceneDev sc, RefCam
                                                            float* __restrict__ tuv) {
   extern __shared__ int smemStack[];
   int* stk = smemStack + threadIdx.x;
+  int* list = smemStack + max(sc.stackDepth, 1) * LT_BLOCK + threadIdx.x;
   int px, py;
   if (!thread_pixel(width, height, px, py)) return;
   LtCounters cnt = {0, 0, 0};
   float fx, fy;
   Trav t;
   t.r = camera_ray(cam, px, py, width, height, fx, fy);
-  trace<false>(t, sc, -1, lt_tinit(kernel), lt_eps(kernel), false, stk, cnt);
+  trace<false>(t, sc, -1, lt_tinit(kernel), lt_eps(kernel), false, stk, list, cnt);
   const Hit h = t.h;
   long long i = (long long)py * width + px;
   if (ids) ids[i] = h.prim;
@@ -854,7 +887,7 @@ int lt_launch_reflatten(const RefNode* dNodes, int nodeCount, const RefPrim* dPr
 
 static size_t stack_bytes(const LtSceneDev& sc) {
   int d = sc.stackDepth < 1 ? 1 : sc.stackDepth;
-  return (size_t)d * LT_BLOCK * sizeof(int);
+  return (size_t)(d + LT_MAX_BATCH) * LT_BLOCK * sizeof(int);
 }
 
 static int tile_blocks(int width, int height) { return ((width + 15) / 16) * ((height + 7) / 8); }

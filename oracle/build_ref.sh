@@ -35,4 +35,14 @@ sed "s|$PAT|outputColor = make_float3(__int_as_float(rayPayload.hitType + 1), ra
   > "$OUT/resources/kernels/cuda/id_dump_b.cu"
 grep -q '__int_as_float(rayPayload.primitiveIndex' "$OUT/resources/kernels/cuda/id_dump_a.cu"
 grep -q '__int_as_float(rayPayload.hitType' "$OUT/resources/kernels/cuda/id_dump_b.cu"
+# the reference's own custom_kernel example, compiled UNCHANGED against this repo's headers and library
+# (drop-in check, run by tests/test_gpu_host_api.py on the GPU box)
+ROOT="$(cd "$HERE/.." && pwd)"
+if [ -f "$ROOT/lens_trace_b200/liblenstrace.so" ]; then
+  mkdir -p "$OUT/bin"
+  /usr/bin/g++ -I"$ROOT/include" "$REF/examples/custom_kernel/src/main.cpp" -o "$OUT/bin/ref_custom_kernel" \
+    -L"$ROOT/lens_trace_b200" -llenstrace -llt_b200 -Wl,-rpath,'$ORIGIN/../../../lens_trace_b200'
+  /usr/bin/g++ -DCUDA_ENABLED -DOPENCL_ENABLED -I"$ROOT/include" "$REF/src/main.cpp" -o "$OUT/bin/ref_LensTrace" \
+    -L"$ROOT/lens_trace_b200" -llenstrace -llt_b200 -Wl,-rpath,'$ORIGIN/../../../lens_trace_b200'
+fi
 echo "built $OUT/libltref.so"

@@ -110,3 +110,33 @@ def test_scene_file_end_to_end():
     want = O.render(L.KERNEL_BASIC_CU, util.scene("cornell_box"), util.default_camera(), 2048, 2048, rows=(1000, 1016),
                     threads=0)
     util.assert_bit_equal(out[1000:1016], want[1000:1016])
+
+
+def test_reference_example_binaries_run_unchanged(tmp_path):
+    """The reference's examples/custom_kernel/src/main.cpp and src/main.cpp, compiled without edits against
+    this repo's headers and liblenstrace.so (oracle/build_ref.sh), run on the B200 path."""
+    import subprocess
+    exe = os.path.join(util.ROOT, "oracle", "_ref", "bin", "ref_custom_kernel")
+    cli = os.path.join(util.ROOT, "oracle", "_ref", "bin", "ref_LensTrace")
+    if not (os.path.exists(exe) and os.path.exists(cli)):
+        pytest.skip("oracle/_ref/bin not built")
+    # the example resolves resources/kernels/custom_opencl.cl and resources/models/cornell_box.obj from the CWD
+    work = tmp_path / "custom_kernel"
+    (work / "resources" / "kernels").mkdir(parents=True)
+    os.symlink(os.path.join(util.ROOT, "resources", "models"), work / "resources" / "models")
+    os.symlink(os.path.join(util.ROOT, "examples", "custom_kernel", "resources", "kernels", "custom_opencl.cl"),
+               work / "resources" / "kernels" / "custom_opencl.cl")
+    r = subprocess.run([exe], cwd=work, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    ppm = (work / "output.jpg.ppm").read_bytes()
+    assert ppm.startswith(b"P6\n800 800\n255\n")
+    pixels = np.frombuffer(ppm[len(b"P6\n800 800\n255\n"):], dtype=np.uint8).reshape(800, 800, 3)
+    want = O.render(L.KERNEL_CUSTOM_BARY, util.scene("cornell_box"), util.default_camera(), 800, 800, threads=0)
+    np.testing.assert_array_equal(pixels, (want * 255).astype(np.int8).view(np.uint8))
+    # the command-line program on a scene file of this repo (2048x2048, basic.cu pipeline)
+    r = subprocess.run([cli, "resources/scenes/basic_cuda.scene"], cwd=util.ROOT, capture_output=True, text=True,
+                       timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    out = os.path.join(util.ROOT, "output.jpg.ppm")
+    assert os.path.getsize(out) > 2048 * 2048 * 3
+    os.remove(out)

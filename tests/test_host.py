@@ -155,3 +155,17 @@ def test_scene_files_parse(tmp_path):
     assert rc == -1
     for f in os.listdir(os.path.join(util.ROOT, "resources", "scenes")):
         json.load(open(os.path.join(util.ROOT, "resources", "scenes", f)))
+
+
+def test_reference_sources_compile_against_these_headers(tmp_path):
+    """Drop-in at the source level: the reference's own example and CLI compile, unedited, against
+    include/lens_trace (needs /root/reference; skipped on the GPU box)."""
+    import subprocess
+    ref = "/root/reference"
+    if not os.path.isdir(ref):
+        pytest.skip("reference sources not present")
+    inc = os.path.join(util.ROOT, "include")
+    for src, defs in ((ref + "/examples/custom_kernel/src/main.cpp", []),
+                      (ref + "/src/main.cpp", ["-DCUDA_ENABLED", "-DOPENCL_ENABLED"])):
+        r = subprocess.run(["/usr/bin/g++", "-fsyntax-only", "-I", inc] + defs + [src], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
