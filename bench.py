@@ -338,6 +338,12 @@ def main():
         else:
             roof = {"bound": "fp32", "achieved": fp32["achieved"], "peak": fp32["peak"], "unit": "T lane-instr/s",
                     "frac": fp32["frac"], "traffic": None}
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            tr = json.load(open(tpath)).get(args.workload)
+            if tr:
+                roof["traffic"] = tr["bytes"]
+                roof["traffic_source"] = tr["capture"]
         roof.update({"kernel": "k_path" if kernel >= 3 else "k_flat", "kernel_ms_per_launch": kernel_ms / args.steps,
                      "algorithmic_bytes_per_launch": alg_bytes, "algorithmic_fp32_instr_per_launch": alg_instr,
                      "node_tests_per_ray": node_tests / rays, "tri_tests_per_ray": tri_tests / rays,

@@ -46,7 +46,7 @@ def assert_images_match(got, want, what, max_outliers=0):
 
 @pytest.mark.parametrize("name", ["green_wall", "cornell_box", "cornell_box_lens", "single", "multi_leaf"])
 @pytest.mark.parametrize("size", [(100, 100), (33, 17), (1, 1), (257, 130)])
-@pytest.mark.parametrize("yaw", [0.0, 0.3, -2.5])
+@pytest.mark.parametrize("yaw", [0.0, 0.04, -0.07, -2.5])  # |yaw| < 0.1 keeps the model in view
 def test_primary_hit_records_bit_exact(ctx, name, size, yaw):
     sb, sc = gpu_scene(ctx, name)
     cam = util.default_camera(yaw)
@@ -61,7 +61,7 @@ def test_primary_hit_records_bit_exact(ctx, name, size, yaw):
 
 @pytest.mark.parametrize("kernel", [L.KERNEL_BASIC_CU, L.KERNEL_BASIC_CL, L.KERNEL_CUSTOM_BARY])
 @pytest.mark.parametrize("name", ["green_wall", "cornell_box", "cornell_box_lens", "single"])
-@pytest.mark.parametrize("yaw", [0.0, 0.2])
+@pytest.mark.parametrize("yaw", [0.0, -0.05, 0.2])
 def test_deterministic_kernels_bit_exact(ctx, kernel, name, yaw):
     sb, sc = gpu_scene(ctx, name)
     cam = util.default_camera(yaw)
@@ -97,7 +97,7 @@ def test_stochastic_single_sample(ctx, kernel, depth, name, frame):
 @pytest.mark.parametrize("mode", [0, 1])
 def test_blend25_kernels(ctx, kernel, mode):
     sb, sc = gpu_scene(ctx, "cornell_box")
-    cam = util.default_camera(0.1, 2)
+    cam = util.default_camera(0.05, 2)
     got = ctx.render(sc, cam, capi.make_params(kernel, 64, 48, kernel_mode=mode, max_ray_depth=3))
     want = O.render(kernel, sb, cam, 64, 48, kernel_mode=mode, max_ray_depth=3, threads=0)
     assert_images_match(got, want, "blend25 kernel %d" % kernel, max_outliers=3)

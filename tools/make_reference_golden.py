@@ -24,7 +24,7 @@ def main():
     os.makedirs(out_dir, exist_ok=True)
     w, h = 96, 72
     for name in ("green_wall", "cornell_box", "cornell_box_lens"):
-        for yaw in (0.0, 0.25):
+        for yaw in (0.0, 0.05):
             world = ab.RefWorld(lib, name)
             color = world.render("basic.cu", w, h, yaw)
             data = dict(nodes=world.sb.nodes, prims=world.sb.prims, materials=world.sb.materials,
