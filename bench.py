@@ -281,6 +281,7 @@ def main():
     if world > 1:
         dist.barrier()
     clocks = sampler.summary()
+    launches_per_step = ctx.stats().kernel_launches
     total_ms = sum(a.elapsed_time(b) for a, b in events)
     kernel_ms = sum(a.elapsed_time(b) for a, b in kernel_events)
     t = torch.tensor([total_ms, kernel_ms], dtype=torch.float64, device=dev)
@@ -344,7 +345,10 @@ def main():
             if tr:
                 roof["traffic"] = tr["bytes"]
                 roof["traffic_source"] = tr["capture"]
-        roof.update({"kernel": "k_path" if kernel >= 3 else "k_flat", "kernel_ms_per_launch": kernel_ms / args.steps,
+        pipeline = "wavefront (k_wf_primary + (k_wf_trace, k_wf_shade) x rounds + k_wf_accumulate)" \
+            if launches_per_step > 1 else ("k_path" if kernel >= 3 else "k_flat")
+        roof.update({"kernel": pipeline, "kernel_ms_per_launch": kernel_ms / args.steps,
+                     "kernels_per_step": launches_per_step,
                      "algorithmic_bytes_per_launch": alg_bytes, "algorithmic_fp32_instr_per_launch": alg_instr,
                      "node_tests_per_ray": node_tests / rays, "tri_tests_per_ray": tri_tests / rays,
                      "fp32_issue": fp32, "node_fetch": fetch,
@@ -364,7 +368,7 @@ def main():
                     "h2d_bytes_per_step": 28, "d2h_bytes_per_step": int(w * h * 3 * 4),
                     "api": "lt_render (C-ABI, host output buffer)" if world == 1 else
                     "lt_render_device + NCCL all-reduce + D2H"},
-            "gpu_launches": args.steps * 1,
+            "gpu_launches": args.steps * launches_per_step,
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -60,8 +60,10 @@ enum lt_accum_mode {
 enum lt_flags {
   LT_FLAG_STATS = 1 << 0, /* count rays / node tests / triangle tests in the reference's traversal order
                              (no any-hit early-out); results via lt_last_stats. Not for timed runs. */
-  LT_FLAG_CULL = 1 << 1   /* opt-in: skip subtrees whose entry distance exceeds the current hit (see DESIGN.md;
-                             identical output is validated, not guaranteed) */
+  LT_FLAG_CULL = 1 << 1,  /* reserved (opt-in culling by hit distance; not implemented: every mode is exact) */
+  LT_FLAG_MEGAKERNEL = 1 << 2, /* stochastic kernels: force the one-thread-per-pixel persistent kernel */
+  LT_FLAG_WAVEFRONT = 1 << 3   /* stochastic kernels: force the wavefront pipeline (default: chosen by size;
+                                  both produce bit-identical output) */
 };
 
 typedef struct lt_ctx lt_ctx;

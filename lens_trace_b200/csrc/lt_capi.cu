@@ -20,6 +20,9 @@ struct lt_ctx {
   float* dOut = nullptr;  // context-owned output / accumulator
   size_t outFloats = 0;
   LtCounters* dCounters = nullptr;
+  void* wfWorkspace = nullptr;  // wavefront path state / ray queues
+  size_t wfBytes = 0;
+  size_t totalMem = 0;
   lt_stats stats = {};
 };
 
@@ -74,6 +77,7 @@ extern "C" int lt_ctx_create(int device_ordinal, lt_ctx** out_ctx) {
   ctx = new lt_ctx();
   ctx->device = device_ordinal;
   ctx->stats.sm_count = prop.multiProcessorCount;
+  ctx->totalMem = prop.totalGlobalMem;
   cudaError_t e2 = cudaStreamCreateWithFlags(&ctx->ownStream, cudaStreamNonBlocking);
   if (e2 == cudaSuccess) e2 = cudaEventCreate(&ctx->ev0);
   if (e2 == cudaSuccess) e2 = cudaEventCreate(&ctx->ev1);
@@ -94,6 +98,7 @@ extern "C" void lt_ctx_destroy(lt_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   if (ctx->dOut) cudaFree(ctx->dOut);
   if (ctx->dCounters) cudaFree(ctx->dCounters);
+  if (ctx->wfWorkspace) cudaFree(ctx->wfWorkspace);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->ownStream) cudaStreamDestroy(ctx->ownStream);
@@ -259,7 +264,8 @@ static int check_params(lt_ctx* ctx, const lt_scene* scene, const void* camera28
   if ((long long)p->width * p->height * p->depth > (1ll << 40)) return fail(ctx, LT_ERR_INVALID, "lt_render: image too large");
   if (p->frames < 1) return fail(ctx, LT_ERR_INVALID, "lt_render: frames must be >= 1");
   if (p->accum_mode < 0 || p->accum_mode > 2) return fail(ctx, LT_ERR_INVALID, "lt_render: bad accum_mode");
-  if (p->max_ray_depth < 0) return fail(ctx, LT_ERR_INVALID, "lt_render: max_ray_depth < 0");
+  if (p->max_ray_depth < 0 || p->max_ray_depth > 255)
+    return fail(ctx, LT_ERR_INVALID, "lt_render: max_ray_depth must be in [0, 255]");
   L->kernel = p->kernel;
   L->kernelMode = p->kernel_mode ? 1 : 0;
   L->width = p->width;
@@ -292,6 +298,17 @@ static int check_params(lt_ctx* ctx, const lt_scene* scene, const void* camera28
     }
     L->batchAnyHit = bAny;
     L->batchClosest = bClosest;
+    static int iterNodes = -1, iterTris = -1;
+    if (iterNodes < 0) {
+      const char* e = getenv("LT_ITER_NODE_STEPS");
+      iterNodes = e ? atoi(e) : 8;
+      e = getenv("LT_ITER_TRI_TESTS");
+      iterTris = e ? atoi(e) : 2;
+      if (iterNodes < 1) iterNodes = 1;
+      if (iterTris < 1) iterTris = 1;
+    }
+    L->iterNodeSteps = iterNodes;
+    L->iterTriTests = iterTris;
   }
   memcpy(&L->cam, camera28, sizeof(RefCamera));
   return LT_OK;
@@ -312,8 +329,45 @@ static int render_common(lt_ctx* ctx, lt_scene* scene, const LtLaunch& L, float*
   CK(cudaSetDevice(ctx->device));
   bool stats = (L.flags & LT_FLAG_STATS) != 0;
   if (stats) CK(cudaMemsetAsync(ctx->dCounters, 0, sizeof(LtCounters), ctx->stream));
+  // stochastic kernels: wavefront pipeline for large launches, persistent megakernel for small ones
+  bool wavefront = false;
+  int batchFrames = 1;
+  if (L.kernel >= 3 && !(L.flags & LT_FLAG_MEGAKERNEL)) {
+    long long pixels = (long long)L.width * L.height;
+    static long long minPaths = -1, maxPaths = -1;
+    if (minPaths < 0) {
+      const char* e = getenv("LT_WAVEFRONT_MIN_PATHS");
+      minPaths = e ? atoll(e) : (1ll << 18);
+      e = getenv("LT_WAVEFRONT_MAX_PATHS");
+      maxPaths = e ? atoll(e) : (1ll << 24);
+    }
+    wavefront = (L.flags & LT_FLAG_WAVEFRONT) || pixels * L.frames >= minPaths;
+    if (wavefront) {
+      long long cap = maxPaths;
+      long long memCap = (long long)(ctx->totalMem / 8) / 200;  // at most 1/8 of the device for the workspace
+      if (cap > memCap) cap = memCap;
+      batchFrames = (int)(cap / pixels);
+      if (batchFrames < 1) batchFrames = 1;
+      if (batchFrames > L.frames) batchFrames = L.frames;
+      size_t need = lt_wf_workspace_bytes_padded((long long)batchFrames * pixels);
+      if (ctx->wfBytes < need) {
+        if (ctx->wfWorkspace) cudaFree(ctx->wfWorkspace);
+        ctx->wfWorkspace = nullptr;
+        ctx->wfBytes = 0;
+        if (cudaMalloc(&ctx->wfWorkspace, need) != cudaSuccess) {
+          cudaGetLastError();
+          if (L.flags & LT_FLAG_WAVEFRONT) return fail(ctx, LT_ERR_CUDA, "lt_render: cannot allocate the wavefront workspace");
+          wavefront = false;  // not a fallback to other arithmetic: the megakernel is the same path per pixel
+        } else {
+          ctx->wfBytes = need;
+        }
+      }
+    }
+  }
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
-  int launches = lt_launch_render(scene->dev, L, dOut, ctx->dCounters, ctx->stream);
+  int launches = wavefront ? lt_launch_render_wavefront(scene->dev, L, dOut, ctx->dCounters, ctx->wfWorkspace,
+                                                        batchFrames, ctx->stats.sm_count, ctx->stream)
+                           : lt_launch_render(scene->dev, L, dOut, ctx->dCounters, ctx->stream);
   CK(cudaGetLastError());
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
   ctx->stats.kernel_launches = launches;

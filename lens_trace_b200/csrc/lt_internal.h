@@ -92,6 +92,8 @@ struct LtLaunch {
   int refillThreshold;  // k_path: leave the traversal loop when fewer lanes than this still have a ray
   int batchAnyHit;      // k_path: leaves recorded before a shadow ray tests them (early-out granularity)
   int batchClosest;     // k_path: leaves recorded before a closest-hit ray tests them
+  int iterNodeSteps;    // trav_iter: box-pair tests per iteration of a persistent loop
+  int iterTriTests;     // trav_iter: triangle tests per iteration
   RefCamera cam;
 };
 
@@ -112,3 +114,8 @@ int lt_launch_primary_hits(const LtSceneDev& sc, const RefCamera& cam, int kerne
 int lt_launch_debug_random(const float* fx, const float* fy, const float* seed, int n, float* out, cudaStream_t stream);
 int lt_launch_debug_hemisphere(const float* u1, const float* u2, const float* up, int n, float* out,
                                cudaStream_t stream);
+
+// wavefront pipeline (lt_wavefront.cu)
+size_t lt_wf_workspace_bytes_padded(long long nPaths);
+int lt_launch_render_wavefront(const LtSceneDev& sc, const LtLaunch& L, float* dOut, LtCounters* dCounters,
+                               void* workspace, int batchFrames, int smCount, cudaStream_t stream);

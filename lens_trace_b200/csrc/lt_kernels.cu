@@ -14,400 +14,9 @@
 //  * All FP32 arithmetic is written with explicit round-to-nearest intrinsics in the operation
 //    order the reference compiles to, so results do not depend on compiler contraction.
 //  * Tensor cores are not used: nothing here is a dense contraction.
-#include "lt_internal.h"
+#include "lt_device.cuh"
 
 #include <cub/device/device_scan.cuh>
-#include <float.h>
-#include <math.h>
-
-#define LT_BLOCK 128
-
-// ------------------------------------------------------------------------------------------------
-// exact-arithmetic helpers: never contracted, independent of -fmad
-// ------------------------------------------------------------------------------------------------
-#define FADD(a, b) __fadd_rn((a), (b))
-#define FSUB(a, b) __fsub_rn((a), (b))
-#define FMUL(a, b) __fmul_rn((a), (b))
-#define FFMA(a, b, c) __fmaf_rn((a), (b), (c))
-#define FRCP(a) __frcp_rn((a))
-#define FDIV(a, b) __fdiv_rn((a), (b))
-#define FSQRT(a) __fsqrt_rn((a))
-
-struct Ray {
-  float ox, oy, oz;
-  float dx, dy, dz;
-};
-
-struct Hit {
-  float t, u, v;
-  int prim;  // primitiveIndex (0 when nothing was hit, as in the reference payload)
-  int hit;   // hitType
-};
-
-// dot as basic.cu:71 compiles: fma(z,z', fma(x,x', y*y')) + 0.0f
-__device__ __forceinline__ float dot3z(float ax, float ay, float az, float bx, float by, float bz) {
-  return FADD(FFMA(az, bz, FFMA(ax, bx, FMUL(ay, by))), 0.0f);
-}
-
-// intersectBounds, basic.cu:136-154: lo/hi are the dirIsNeg-selected bounds per axis.
-__device__ __forceinline__ bool slab(float lox, float hix, float loy, float hiy, float loz, float hiz,
-                                     const Ray& r, float ix, float iy, float iz) {
-  float tx0 = FMUL(FSUB(lox, r.ox), ix);
-  float tx1 = FMUL(FSUB(hix, r.ox), ix);
-  float ty0 = FMUL(FSUB(loy, r.oy), iy);
-  float ty1 = FMUL(FSUB(hiy, r.oy), iy);
-  float tz0 = FMUL(FSUB(loz, r.oz), iz);
-  float tz1 = FMUL(FSUB(hiz, r.oz), iz);
-  bool miss1 = (tx0 > ty1) || (ty0 > tx1);
-  float a = (ty0 > tx0) ? ty0 : tx0;
-  float b = (ty1 < tx1) ? ty1 : tx1;
-  bool miss2 = (a > tz1) || (tz0 > b);
-  float b2 = (tz1 < b) ? tz1 : b;
-  return !miss1 && !miss2 && (b2 > 0.0f);
-}
-
-// intersectTriangle, basic.cu:93-134, on the pre-subtracted record.  Returns true when the hit
-// record was replaced (strict t < best, no t > 0 test -- both as in the reference).
-__device__ __forceinline__ bool tri_test(const LtTri* __restrict__ tris, int prim, const Ray& r, float epsThr,
-                                         Hit& h) {
-  const float4* tp = reinterpret_cast<const float4*>(tris + prim);
-  float4 q0 = __ldg(tp), q1 = __ldg(tp + 1), q2 = __ldg(tp + 2);
-  float ax = q0.x, ay = q0.y, az = q0.z;
-  float e1x = q0.w, e1y = q1.x, e1z = q1.y;
-  float e2x = q1.z, e2y = q1.w, e2z = q2.x;
-  float pvx = FFMA(r.dy, e2z, -FMUL(r.dz, e2y));
-  float pvy = FFMA(r.dz, e2x, -FMUL(r.dx, e2z));
-  float pvz = FFMA(r.dx, e2y, -FMUL(r.dy, e2x));
-  float det = dot3z(e1x, e1y, e1z, pvx, pvy, pvz);
-  if (fabsf(det) < epsThr) return false;
-  float inv = FRCP(det);
-  float tx = FSUB(r.ox, ax), ty = FSUB(r.oy, ay), tz = FSUB(r.oz, az);
-  float u = FMUL(dot3z(tx, ty, tz, pvx, pvy, pvz), inv);
-  if (u < 0.0f || u > 1.0f) return false;
-  float qx = FFMA(ty, e1z, -FMUL(tz, e1y));
-  float qy = FFMA(tz, e1x, -FMUL(tx, e1z));
-  float qz = FFMA(tx, e1y, -FMUL(ty, e1x));
-  float v = FMUL(dot3z(r.dx, r.dy, r.dz, qx, qy, qz), inv);
-  if (v < 0.0f || FADD(u, v) > 1.0f) return false;
-  float t = FMUL(dot3z(e2x, e2y, e2z, qx, qy, qz), inv);
-  if (t < h.t) {
-    h.t = t;
-    h.u = u;
-    h.v = v;
-    return true;
-  }
-  return false;
-}
-
-// The same test for rays whose origin and direction reciprocals are all finite (every ray but the
-// axis-parallel ones).  Without NaNs the select chain above is an interval test:
-// hit <=> max(lo) <= min(hi) && min(hi) > 0, and (bound-o)*inv is monotonic in the bound, so the
-// dirIsNeg-selected lo/hi are min/max of the two products.  Same FSUB/FMUL, so same decisions.
-__device__ __forceinline__ bool slab_fast(float mnx, float mxx, float mny, float mxy, float mnz, float mxz,
-                                          const Ray& r, float ix, float iy, float iz) {
-  float ax = FMUL(FSUB(mnx, r.ox), ix), bx = FMUL(FSUB(mxx, r.ox), ix);
-  float ay = FMUL(FSUB(mny, r.oy), iy), by = FMUL(FSUB(mxy, r.oy), iy);
-  float az = FMUL(FSUB(mnz, r.oz), iz), bz = FMUL(FSUB(mxz, r.oz), iz);
-  float lo = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
-  float hi = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
-  return lo <= hi && hi > 0.0f;
-}
-
-// intersect / intersectIgnorePrimitiveIndex (basic.cu:156-243) on the child-pair layout, as a
-// resumable state machine.  Visits children near-first by the sign of the ray direction on the
-// split axis and defers the far child, so triangles are tested in exactly the reference's order; a
-// child whose box is missed is never pushed.  anyHit = stop at the first accepted triangle: exact
-// for shadow rays because the callers read only hitType (basic_lighting.cl:272,
-// global_illumination.cl:296,352).
-#define LT_EXACT_SLAB 8u  // negMask bit: ray has a non-finite reciprocal/origin -> select-chain slab test
-
-struct Trav {
-  Ray r;
-  float ix, iy, iz;
-  unsigned negMask;  // bit k: direction reciprocal on axis k is negative; LT_EXACT_SLAB
-  int cur;           // >= 0 wide node, < 0 leaf (~primitive), LT_DONE finished
-  int sp;
-  int ignore;        // intersectIgnorePrimitiveIndex's primitive, < 0 = none
-  bool anyHit;
-  Hit h;
-};
-
-__device__ __forceinline__ bool finite3(float a, float b, float c) {
-  return fabsf(a) <= FLT_MAX && fabsf(b) <= FLT_MAX && fabsf(c) <= FLT_MAX;
-}
-
-__device__ __forceinline__ bool box_test(const Trav& t, float mnx, float mxx, float mny, float mxy, float mnz,
-                                         float mxz) {
-  if (t.negMask & LT_EXACT_SLAB) {
-    bool nx = t.negMask & 1u, ny = t.negMask & 2u, nz = t.negMask & 4u;
-    return slab(nx ? mxx : mnx, nx ? mnx : mxx, ny ? mxy : mny, ny ? mny : mxy, nz ? mxz : mnz, nz ? mnz : mxz, t.r,
-                t.ix, t.iy, t.iz);
-  }
-  return slab_fast(mnx, mxx, mny, mxy, mnz, mxz, t.r, t.ix, t.iy, t.iz);
-}
-
-template <bool STATS>
-__device__ __forceinline__ void trav_begin(Trav& t, const LtSceneDev& sc, int ignore, float tInit, bool anyHit,
-                                           LtCounters& cnt) {
-  t.ix = FRCP(t.r.dx);
-  t.iy = FRCP(t.r.dy);
-  t.iz = FRCP(t.r.dz);
-  t.negMask = (t.ix < 0.0f ? 1u : 0u) | (t.iy < 0.0f ? 2u : 0u) | (t.iz < 0.0f ? 4u : 0u);
-  if (!(finite3(t.ix, t.iy, t.iz) && finite3(t.r.ox, t.r.oy, t.r.oz))) t.negMask |= LT_EXACT_SLAB;
-  t.h.t = tInit; t.h.u = 0.0f; t.h.v = 0.0f; t.h.prim = 0; t.h.hit = 0;
-  t.ignore = ignore;
-  t.anyHit = STATS ? false : anyHit;
-  t.sp = 0;
-  if (STATS) {
-    cnt.rays++;
-    cnt.nodeTests++;
-  }
-  // root box (reference node 0)
-  bool hit = box_test(t, sc.rootMin[0], sc.rootMax[0], sc.rootMin[1], sc.rootMax[1], sc.rootMin[2], sc.rootMax[2]);
-  t.cur = hit ? sc.rootRef : LT_DONE;
-  if (STATS && hit && t.cur < 0 && sc.rootCount > 1 && ~t.cur != ignore) cnt.triTests += (unsigned)(sc.rootCount - 1);
-}
-
-__device__ __forceinline__ int trav_pop(Trav& t, const int* __restrict__ stk) {
-  if (t.sp > 0) {
-    t.sp--;
-    return stk[t.sp * LT_BLOCK];
-  }
-  return LT_DONE;
-}
-
-// one inner-node step; requires t.cur >= 0
-template <bool STATS>
-__device__ __forceinline__ void trav_node_step(Trav& t, const LtSceneDev& sc, int* __restrict__ stk, LtCounters& cnt) {
-  const float4* np = reinterpret_cast<const float4*>(sc.wnodes + t.cur);
-  float4 bx = __ldg(np), by = __ldg(np + 1), bz = __ldg(np + 2);
-  int4 m = __ldg(reinterpret_cast<const int4*>(np) + 3);
-  bool hl = box_test(t, bx.x, bx.y, by.x, by.y, bz.x, bz.y);
-  bool hr = box_test(t, bx.z, bx.w, by.z, by.w, bz.z, bz.w);
-  if (STATS) {
-    cnt.nodeTests += 2;
-    // a leaf with primitiveCount n is tested n times by the reference (always the same triangle)
-    unsigned lc = (unsigned)m.w & 0xffffu, rc = (unsigned)m.w >> 16;
-    if (hl && m.x < 0 && lc > 1 && ~m.x != t.ignore) cnt.triTests += lc - 1;
-    if (hr && m.y < 0 && rc > 1 && ~m.y != t.ignore) cnt.triTests += rc - 1;
-  }
-  bool axisNeg = (t.negMask >> m.z) & 1u;
-  int nearRef = axisNeg ? m.y : m.x, farRef = axisNeg ? m.x : m.y;
-  bool hn = axisNeg ? hr : hl, hf = axisNeg ? hl : hr;
-  if (hn) {
-    t.cur = nearRef;
-    if (hf) {
-      stk[t.sp * LT_BLOCK] = farRef;
-      t.sp++;
-    }
-  } else if (hf) {
-    t.cur = farRef;
-  } else {
-    t.cur = trav_pop(t, stk);
-  }
-}
-
-// Traversal never depends on triangle results (the reference does not cull by t, basic.cu:136-154),
-// so box tests and triangle tests are decoupled: the node phase walks the tree and only RECORDS the
-// leaves it reaches, in order, in a small per-thread list in shared memory; the leaf phase then
-// tests the recorded triangles in that order.  A warp therefore switches between "all lanes test
-// boxes" and "all lanes test triangles" once per batch instead of at every leaf.
-#define LT_MAX_BATCH 16  // list entries per thread (shared memory: [LT_MAX_BATCH][LT_BLOCK] ints)
-
-// node phase: advance until the ray is exhausted (t.cur == LT_DONE) or `batch` leaves are recorded.
-// Returns the number of recorded leaves.
-template <bool STATS>
-__device__ __forceinline__ int trav_collect(Trav& t, const LtSceneDev& sc, int* __restrict__ stk,
-                                            int* __restrict__ list, int batch, LtCounters& cnt) {
-  int n = 0;
-  while (t.cur != LT_DONE && n < batch) {
-    if (t.cur >= 0) {
-      trav_node_step<STATS>(t, sc, stk, cnt);
-    } else {
-      int prim = ~t.cur;
-      if (prim != t.ignore) {
-        list[n * LT_BLOCK] = prim;
-        n++;
-      }
-      t.cur = trav_pop(t, stk);
-    }
-  }
-  return n;
-}
-
-// leaf phase: test the recorded triangles in order.  Returns true if the ray is finished early
-// (any-hit ray that found a hit).
-template <bool STATS>
-__device__ __forceinline__ bool trav_test(Trav& t, const LtSceneDev& sc, const int* __restrict__ list, int n,
-                                          float epsThr, LtCounters& cnt) {
-  for (int i = 0; i < n; i++) {
-    int prim = list[i * LT_BLOCK];
-    if (STATS) cnt.triTests++;
-    if (tri_test(sc.tris, prim, t.r, epsThr, t.h)) {
-      t.h.prim = prim;
-      t.h.hit = 1;
-      if (t.anyHit) {
-        t.cur = LT_DONE;
-        return true;
-      }
-    }
-  }
-  return false;
-}
-
-// run one ray to completion (deterministic kernels, hit-record kernel)
-template <bool STATS>
-__device__ __forceinline__ void trace(Trav& t, const LtSceneDev& sc, int ignore, float tInit, float epsThr,
-                                      bool anyHit, int* __restrict__ stk, int* __restrict__ list, LtCounters& cnt) {
-  trav_begin<STATS>(t, sc, ignore, tInit, anyHit, cnt);
-  while (t.cur != LT_DONE) {
-    int n = trav_collect<STATS>(t, sc, stk, list, LT_MAX_BATCH, cnt);
-    trav_test<STATS>(t, sc, list, n, epsThr, cnt);
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// per-kernel constants (see oracle/lt_oracle.c: flavour_for_kernel)
-// ------------------------------------------------------------------------------------------------
-__host__ __device__ inline float lt_tinit(int kernel) { return kernel == 0 ? 10000000.0f : FLT_MAX; }
-__host__ __device__ inline float lt_eps(int kernel) {
-  // fabs(det) < eps; the macro-defined epsilons are compared in fp64, i.e. against the next float up
-  switch (kernel) {
-    case 0: case 1: case 2: return 0x1.ad7f2ap-24f;  // (float)1e-7: basic.cu:95, basic.cl:78
-    case 3: return 0x1.ad7f2ap-24f;                   // (float)1e-7 >= 1e-7 (double) already
-    default: return 0x1.a36e30p-14f;                  // smallest float >= 1e-4 (double); (float)1e-4 is below
-  }
-}
-
-// camera ray, basic.cu:350-358; fused forms as NVRTC+ptxas emit them (oracle/notes_fma_order.md)
-__device__ __forceinline__ Ray camera_ray(const RefCamera& cam, int px, int py, int width, int height, float& fx,
-                                          float& fy) {
-  fx = FADD(FDIV((float)px, (float)width), -0.5f);
-  fy = FADD(FDIV((float)py, (float)height), -0.5f);
-  float c = cosf(cam.yaw), s = sinf(cam.yaw);
-  float dx0 = FSUB(0.0f, fx);
-  Ray r;
-  r.ox = FADD(fx, cam.position[0]);
-  r.oy = FADD(fy, cam.position[1]);
-  r.oz = FADD(cam.position[2], 0.0f);
-  r.dx = FFMA(dx0, c, FMUL(s, 5.0f));
-  r.dy = FSUB(0.0f, fy);
-  r.dz = FFMA(c, 5.0f, -FMUL(dx0, s));
-  return r;
-}
-
-__device__ __forceinline__ float bary0(float u, float v) {
-  return (float)__dsub_rn(__dsub_rn(1.0, (double)u), (double)v);
-}
-
-// thread -> pixel: a warp covers an 8x4 pixel tile, a block 16x8 (coherent primary rays).
-__device__ __forceinline__ bool thread_pixel(int width, int height, int& px, int& py) {
-  int tilesX = (width + 15) >> 4;
-  int tile = blockIdx.x;
-  int tyi = tile / tilesX, txi = tile - tyi * tilesX;
-  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  px = (txi << 4) + ((warp & 1) << 3) + (lane & 7);
-  py = (tyi << 3) + ((warp >> 1) << 2) + (lane >> 3);
-  return px < width && py < height;
-}
-
-// running mean / weighted sum / plain store of one finished frame
-struct FrameSink {
-  float acc[3];
-  __device__ __forceinline__ void begin(const LtLaunch& L, const float* out, long long id) {
-    acc[0] = acc[1] = acc[2] = 0.0f;
-    bool needPrev = (L.accumMode == 2) || (L.accumMode == 1 && L.cam.frameCount > 0);
-    if (needPrev) {
-      acc[0] = out[id + 0];
-      acc[1] = out[id + 1];
-      acc[2] = out[id + 2];
-    }
-  }
-  // accumulator.frag:10-19: color = (sample + prev*frameCount) / (frameCount + 1) when frameCount > 0
-  __device__ __forceinline__ void frame(const LtLaunch& L, unsigned frameCount, const float c[3]) {
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-      if (L.accumMode == 1) {
-        float v = c[k];
-        if (frameCount > 0) v = FDIV(FADD(v, FMUL(acc[k], (float)frameCount)), (float)(frameCount + 1u));
-        acc[k] = v;
-      } else if (L.accumMode == 2) {
-        acc[k] = FADD(acc[k], FMUL(L.accumWeight, c[k]));
-      } else {
-        acc[k] = c[k];
-      }
-    }
-  }
-  __device__ __forceinline__ void end(float* out, long long id) const {
-    out[id + 0] = acc[0];
-    out[id + 1] = acc[1];
-    out[id + 2] = acc[2];
-  }
-};
-
-__device__ __forceinline__ void flush_counters(LtCounters* g, const LtCounters& c) {
-  if (g) {
-    atomicAdd(&g->rays, c.rays);
-    atomicAdd(&g->nodeTests, c.nodeTests);
-    atomicAdd(&g->triTests, c.triTests);
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// kernel 1: deterministic pipelines -- basic (flat diffuse + lens refraction) and custom barycentric
-// ------------------------------------------------------------------------------------------------
-// barycentric interpolation as basic.cu:257-265 compiles: fma(v, C, fma(A, w0, u*B))
-__device__ __forceinline__ void lerp_fused(const float* a, const float* b, const float* c, float w0, float u,
-                                           float v, float out[3]) {
-#pragma unroll
-  for (int k = 0; k < 3; k++) out[k] = FFMA(v, c[k], FFMA(a[k], w0, FMUL(u, b[k])));
-}
-
-// traceRayThroughLens + refract, basic.cu:79-86,245-298 (operation order: oracle/notes_fma_order.md)
-// On entry t holds the primary ray and its hit; on exit the refracted ray and its hit.
-template <bool STATS>
-__device__ void lens_path(const LtSceneDev& sc, Trav& t, float tInit, float epsThr, int* stk, int* list,
-                          LtCounters& cnt) {
-  const RefPrim* prim = sc.prims + t.h.prim;
-  const RefMaterial* mat = sc.mats + prim->materialIndex;
-  int firstPrim = t.h.prim;
-  float w0 = bary0(t.h.u, t.h.v);
-  float pos[3], nrm[3];
-  lerp_fused(prim->a, prim->b, prim->c, w0, t.h.u, t.h.v, pos);
-  lerp_fused(prim->na, prim->nb, prim->nc, w0, t.h.u, t.h.v, nrm);
-
-  float n = FRCP(mat->ior);
-  float c = dot3z(t.r.dx, t.r.dy, t.r.dz, nrm[0], nrm[1], nrm[2]);
-  float sinT2 = (float)__dmul_rn(__dsub_rn(1.0, (double)FMUL(c, c)), (double)FMUL(n, n));
-  float cosT = (float)__dsqrt_rn(__dsub_rn(1.0, (double)sinT2));
-  float k = FFMA(c, -n, -cosT);
-  float dx = FFMA(t.r.dx, n, FMUL(nrm[0], k));
-  float dy = FFMA(t.r.dy, n, FMUL(nrm[1], k));
-  float dz = FFMA(t.r.dz, n, FMUL(nrm[2], k));
-  float r2w = FFMA(n, 0.0f, FMUL(k, 0.0f));
-  t.r.ox = pos[0]; t.r.oy = pos[1]; t.r.oz = pos[2];
-  t.r.dx = dx; t.r.dy = dy; t.r.dz = dz;
-  trace<STATS>(t, sc, firstPrim, tInit, epsThr, false, stk, list, cnt);
-
-  int secondPrim = t.h.prim;
-  prim = sc.prims + secondPrim;
-  mat = sc.mats + prim->materialIndex;
-  w0 = bary0(t.h.u, t.h.v);
-  lerp_fused(prim->a, prim->b, prim->c, w0, t.h.u, t.h.v, pos);
-  lerp_fused(prim->na, prim->nb, prim->nc, w0, t.h.u, t.h.v, nrm);
-
-  float ior = mat->ior;
-  float c2 = FFMA(0.0f, r2w, FFMA(-t.r.dz, nrm[2], FFMA(t.r.dx, -nrm[0], -FMUL(t.r.dy, nrm[1]))));
-  float sinT2b = (float)__dmul_rn(__dsub_rn(1.0, (double)FMUL(c2, c2)), (double)FMUL(ior, ior));
-  float cosTb = (float)__dsqrt_rn(__dsub_rn(1.0, (double)sinT2b));
-  float k2 = FFMA(c2, -ior, -cosTb);
-  dx = FFMA(t.r.dx, ior, -FMUL(k2, nrm[0]));
-  dy = FFMA(t.r.dy, ior, -FMUL(k2, nrm[1]));
-  dz = FFMA(t.r.dz, ior, -FMUL(k2, nrm[2]));
-  t.r.ox = pos[0]; t.r.oy = pos[1]; t.r.oz = pos[2];
-  t.r.dx = dx; t.r.dy = dy; t.r.dz = dz;
-  trace<STATS>(t, sc, secondPrim, tInit, epsThr, false, stk, list, cnt);
-}
 
 template <bool STATS>
 __global__ void __launch_bounds__(LT_BLOCK) k_flat(LtSceneDev sc, LtLaunch L, float* __restrict__ out,
@@ -454,105 +63,6 @@ __global__ void __launch_bounds__(LT_BLOCK) k_flat(LtSceneDev sc, LtLaunch L, fl
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// kernel 2: stochastic pipelines -- direct lighting, accumulator, global illumination
-// ------------------------------------------------------------------------------------------------
-// fmod(x, M_PI) bit-exact: q is within one of the true quotient, fma gives the exact remainder
-// (both x and q*pi are multiples of 2^-51 and the result is < 2*pi), then one exact correction.
-__device__ __forceinline__ double fmod_pi(double x) {
-  const double PI = 3.14159265358979323846;
-  double ax = fabs(x);
-  double r = ax;
-  if (ax >= PI) {
-    double q = floor(__dmul_rn(ax, 0.31830988618379067154));
-    r = __fma_rn(-q, PI, ax);
-    if (r < 0.0) r = __dadd_rn(r, PI);
-    else if (r >= PI) r = __dsub_rn(r, PI);
-  }
-  return copysign(r, x);
-}
-
-// random(), basic_lighting.cl:64-67
-__device__ __forceinline__ float lt_random(float fx, float fy, float seed) {
-  float d = FADD(FMUL(fx, 12.9898f), FMUL(fy, 78.233f));
-  double x = __dadd_rn((double)d, __dmul_rn(1113.1, (double)seed));
-  float a = (float)__dmul_rn(sin(fmod_pi(x)), 43758.5453);
-  return FSUB(a, floorf(a));
-}
-
-__device__ __forceinline__ float len3(float x, float y, float z) {
-  return FSQRT(FADD(FADD(FMUL(x, x), FMUL(y, y)), FMUL(z, z)));
-}
-__device__ __forceinline__ float dot3plain(const float a[3], const float b[3]) {
-  return FADD(FADD(FMUL(a[0], b[0]), FMUL(a[1], b[1])), FMUL(a[2], b[2]));
-}
-// basic_lighting.cl:236-244 / global_illumination.cl:235-240 (no contraction)
-__device__ __forceinline__ void lerp_plain(const float* a, const float* b, const float* c, float w0, float u,
-                                           float v, float out[3]) {
-#pragma unroll
-  for (int k = 0; k < 3; k++) out[k] = FADD(FADD(FMUL(a[k], w0), FMUL(b[k], u)), FMUL(c[k], v));
-}
-
-__device__ __forceinline__ bool is_light(const LtSceneDev& sc, int prim) {
-  bool hit = false;
-  unsigned n = min(sc.lights->count, 64u);
-  for (unsigned x = 0; x < n; x++) hit = hit || ((unsigned)prim == sc.lights->primitives[x]);
-  return hit;
-}
-
-// light sample: basic_lighting.cl:246-262 with the three random numbers already drawn
-// (rIdx = random(seed), rU = random(seed+1), rV = random(seed+2)).  Overwrites r with the shadow
-// ray (origin = pos, direction = normalize(L - P)) and returns its initial t.
-__device__ __forceinline__ float make_shadow_ray(const LtSceneDev& sc, const float pos[3], float rIdx, float rU,
-                                                 float rV, Ray& sr) {
-  int idx = (int)FMUL(rIdx, (float)sc.lights->count);
-  idx = max(0, min(idx, 63));
-  const RefPrim* lp = sc.prims + sc.lights->primitives[idx];
-  float ux = rU, uy = rV;
-  if (FADD(ux, uy) > 1.0f) {
-    ux = FSUB(1.0f, ux);
-    uy = FSUB(1.0f, uy);
-  }
-  float w0 = bary0(ux, uy);
-  float Lp[3];
-  lerp_plain(lp->a, lp->b, lp->c, w0, ux, uy, Lp);
-  float dx = FSUB(Lp[0], pos[0]), dy = FSUB(Lp[1], pos[1]), dz = FSUB(Lp[2], pos[2]);
-  float len = len3(dx, dy, dz);
-  sr.ox = pos[0]; sr.oy = pos[1]; sr.oz = pos[2];
-  sr.dx = FDIV(dx, len);
-  sr.dy = FDIV(dy, len);
-  sr.dz = FDIV(dz, len);
-  return (float)__dsub_rn((double)len, 0.01);
-}
-
-// uniformSampleHemisphere + alignHemisphereWithCoordinateSystem, global_illumination.cl:69-82
-__device__ __forceinline__ void sample_hemisphere(float u1, float u2, const float up[3], float dir[4]) {
-  float z = u1;
-  float r = FSQRT(fmaxf(0.0f, FSUB(1.0f, FMUL(z, z))));
-  double phi = __dmul_rn(6.28318530717958647692, (double)u2);
-  double sp, cp;
-  sincos(phi, &sp, &cp);
-  float hx = (float)__dmul_rn((double)r, cp);
-  float hy = z;
-  float hz = (float)__dmul_rn((double)r, sp);
-  const float cx = 0.0072f, cy = 1.0f, cz = 0.0034f;
-  float rx = FSUB(FMUL(up[1], cz), FMUL(up[2], cy));
-  float ry = FSUB(FMUL(up[2], cx), FMUL(up[0], cz));
-  float rz = FSUB(FMUL(up[0], cy), FMUL(up[1], cx));
-  float rl = len3(rx, ry, rz);
-  rx = FDIV(rx, rl); ry = FDIV(ry, rl); rz = FDIV(rz, rl);
-  float fwx = FSUB(FMUL(ry, up[2]), FMUL(rz, up[1]));
-  float fwy = FSUB(FMUL(rz, up[0]), FMUL(rx, up[2]));
-  float fwz = FSUB(FMUL(rx, up[1]), FMUL(ry, up[0]));
-  dir[0] = FADD(FADD(FMUL(hx, rx), FMUL(hy, up[0])), FMUL(hz, fwx));
-  dir[1] = FADD(FADD(FMUL(hx, ry), FMUL(hy, up[1])), FMUL(hz, fwy));
-  dir[2] = FADD(FADD(FMUL(hx, rz), FMUL(hy, up[2])), FMUL(hz, fwz));
-  dir[3] = hy;
-}
-
-enum PathStage { ST_PRIMARY = 0, ST_SHADOW_DIRECT = 1, ST_EXTENSION = 2, ST_SHADOW_EXT = 3 };
-
-
 // One thread = one pixel, persistent over all frames and samples of the launch.  The warp alternates
 // between two phases:
 //   S (shade/regenerate): lanes whose ray has finished consume the hit and produce their next ray
@@ -570,12 +80,7 @@ __global__ void __launch_bounds__(LT_BLOCK) k_path(LtSceneDev sc, LtLaunch L, fl
   int px, py;
   bool alive = thread_pixel(L.width, L.height, px, py);
   LtCounters cnt = {0, 0, 0};
-
-  const float tInit = lt_tinit(L.kernel), epsThr = lt_eps(L.kernel);
-  const bool isGI = (L.kernel == 5 || L.kernel == 6);
-  const bool whiteOnLight = (L.kernel == 4);
-  const int samplesPerFrame = (L.kernel == 3 || L.kernel == 5) ? 25 : 1;
-  const int maxDepth = L.maxRayDepth > 0 ? L.maxRayDepth : 16;
+  const PathConsts pc = path_consts(L);
 
   float fx = 0.0f, fy = 0.0f;
   Ray cameraRay = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 1.0f};
@@ -590,145 +95,37 @@ __global__ void __launch_bounds__(LT_BLOCK) k_path(LtSceneDev sc, LtLaunch L, fl
 
   int frame = 0, sample = 0;
   float frameColor[3] = {0.0f, 0.0f, 0.0f};
-  unsigned sampleIndex = (samplesPerFrame == 25) ? L.cam.frameCount * 32u : L.cam.frameCount;
-
-  // per-sample state
-  int stage = ST_PRIMARY;
-  float direct[3] = {0.0f, 0.0f, 0.0f}, indirect[3] = {0.0f, 0.0f, 0.0f};
-  float nrm[3] = {0.0f, 0.0f, 0.0f}, diffuse[3] = {0.0f, 0.0f, 0.0f};
-  float extW = 0.0f;
-  int hitPrim = 0, depth = 0;
+  unsigned sampleIndex = (pc.samplesPerFrame == 25) ? L.cam.frameCount * 32u : L.cam.frameCount;
+  PathState ps;
+  ps.nrm[0] = ps.nrm[1] = ps.nrm[2] = 0.0f;
+  ps.diffuse[0] = ps.diffuse[1] = ps.diffuse[2] = 0.0f;
+  ps.extW = 0.0f;
+  ps.hitPrim = 0;
+  ps.depth = 0;
+  path_reset(ps);
 
   Trav t;
   t.r = cameraRay;
   bool traversing = false;
   if (alive) {
-    trav_begin<STATS>(t, sc, -1, tInit, false, cnt);
+    trav_begin<STATS>(t, sc, -1, pc.tInit, false, cnt);
     traversing = (t.cur != LT_DONE);
   }
 
   while (true) {
     // ---------------- phase S: consume finished rays, generate the next ones ----------------
     while (alive && !traversing) {
+      float tStart;
+      int ignore;
+      bool anyHit;
       const Hit h = t.h;
-      bool sampleDone = false, wantShadow = false, wantExt = false, retrace = false;
-      unsigned seedBase = 0;
-
-      if (stage == ST_PRIMARY || stage == ST_EXTENSION) {
-        // basic_lighting.cl:230-246 / accumulator.cl:233-238 / global_illumination.cl:255-274, 310-331
-        bool lightHit = (stage == ST_EXTENSION || isGI || whiteOnLight) && is_light(sc, h.prim);
-        if (lightHit) {
-          if (stage == ST_PRIMARY) {
-            direct[0] = direct[1] = direct[2] = 1.0f;
-            sampleDone = true;
-          } else {
-            // dot(previousNormal (w = 1), direction (w = hemisphere.y)), global_illumination.cl:321;
-            // the ray is not advanced, so the same hit is found again at the next depth
-            float w = (float)__ddiv_rn(1.0, (double)(depth + 1));
-            float d = FADD(FADD(FADD(FMUL(nrm[0], t.r.dx), FMUL(nrm[1], t.r.dy)), FMUL(nrm[2], t.r.dz)),
-                           FMUL(1.0f, extW));
-            float c = FMUL(FMUL(w, 1.0f), d);
-            indirect[0] = FADD(indirect[0], c); indirect[1] = FADD(indirect[1], c); indirect[2] = FADD(indirect[2], c);
-            depth++;
-            if (depth >= maxDepth) sampleDone = true;
-            else retrace = true;
-          }
-        } else if (h.hit == 1) {
-          const RefPrim* prim = sc.prims + h.prim;
-          const RefMaterial* mat = sc.mats + prim->materialIndex;
-          float w0 = bary0(h.u, h.v);
-          float pos[3];
-          lerp_plain(prim->a, prim->b, prim->c, w0, h.u, h.v, pos);
-          lerp_plain(prim->na, prim->nb, prim->nc, w0, h.u, h.v, nrm);
-          diffuse[0] = mat->diffuse[0]; diffuse[1] = mat->diffuse[1]; diffuse[2] = mat->diffuse[2];
-          hitPrim = h.prim;
-          t.r.ox = pos[0]; t.r.oy = pos[1]; t.r.oz = pos[2];  // origin of the shadow ray and of the next extension
-          wantShadow = true;
-          seedBase = (stage == ST_PRIMARY) ? sampleIndex : sampleIndex + (unsigned)depth + 5u;
-          stage = (stage == ST_PRIMARY) ? ST_SHADOW_DIRECT : ST_SHADOW_EXT;
-        } else {
-          sampleDone = true;
-        }
-      } else {
-        // the shadow ray's direction is positionToLight, its origin the shaded position
-        bool lit = (h.hit == 0);
-        float d = FADD(FADD(FMUL(t.r.dx, nrm[0]), FMUL(t.r.dy, nrm[1])), FMUL(t.r.dz, nrm[2]));
-        if (stage == ST_SHADOW_DIRECT) {  // basic_lighting.cl:272-274, global_illumination.cl:296-309
-          if (lit) {
-            direct[0] = FMUL(diffuse[0], d); direct[1] = FMUL(diffuse[1], d); direct[2] = FMUL(diffuse[2], d);
-          }
-          if (isGI && maxDepth > 0) {
-            wantExt = true;
-            seedBase = sampleIndex + 3u;
-            depth = 0;
-          } else {
-            sampleDone = true;
-          }
-        } else {  // global_illumination.cl:352-365
-          if (lit) {
-            float w = (float)__ddiv_rn(1.0, (double)(depth + 1));
-            indirect[0] = FADD(indirect[0], FMUL(FMUL(w, diffuse[0]), d));
-            indirect[1] = FADD(indirect[1], FMUL(FMUL(w, diffuse[1]), d));
-            indirect[2] = FADD(indirect[2], FMUL(FMUL(w, diffuse[2]), d));
-            seedBase = sampleIndex + (unsigned)depth + 8u;
-            depth++;
-            // the reference still draws a direction at the last depth, but never traces it
-            if (depth >= maxDepth) sampleDone = true;
-            else wantExt = true;
-          } else {
-            sampleDone = true;
-          }
-        }
-      }
-
-      // the hash RNG (fp64 fmod + sin), one code site for every stage
-      float rA = 0.0f, rB = 0.0f, rC = 0.0f;
-      if (wantShadow || wantExt) {
-        rA = lt_random(fx, fy, (float)seedBase);
-        rB = lt_random(fx, fy, (float)(seedBase + 1u));
-        if (wantShadow) rC = lt_random(fx, fy, (float)(seedBase + 2u));
-      }
-
-      int ignore = -1;
-      float tStart = tInit;
-      bool anyHit = false;
-      if (wantShadow) {
-        float pos[3] = {t.r.ox, t.r.oy, t.r.oz};
-        tStart = make_shadow_ray(sc, pos, rA, rB, rC, t.r);
-        ignore = hitPrim;
-        anyHit = true;
-      } else if (wantExt) {  // global_illumination.cl:300-305, 355-361
-        float dir[4];
-        sample_hemisphere(rA, rB, nrm, dir);
-        t.r.dx = dir[0]; t.r.dy = dir[1]; t.r.dz = dir[2];  // origin stays the shaded position
-        extW = dir[3];
-        ignore = hitPrim;
-        stage = ST_EXTENSION;
-      } else if (retrace) {
-        ignore = hitPrim;
-      }
-
-      if (sampleDone) {
-        // GI returns directColor + indirectColor (global_illumination.cl:375); the lighting kernels
-        // return outputColor as is (basic_lighting.cl:277) -- the add would turn -0 into +0
-        float c[3] = {direct[0], direct[1], direct[2]};
-        if (isGI) {
-          c[0] = FADD(direct[0], indirect[0]); c[1] = FADD(direct[1], indirect[1]); c[2] = FADD(direct[2], indirect[2]);
-        }
-        if (samplesPerFrame == 1 || sample == 0) {
-          frameColor[0] = c[0]; frameColor[1] = c[1]; frameColor[2] = c[2];
-        } else {  // basic_lighting.cl:310-316: recency-weighted blend
-          float a = FDIV((float)(25 - sample), 25.0f);
-          float ia = FSUB(1.0f, a);
-#pragma unroll
-          for (int k = 0; k < 3; k++) frameColor[k] = FADD(FMUL(ia, frameColor[k]), FMUL(a, c[k]));
-        }
+      if (shade_step(sc, pc, ps, t.r, h, fx, fy, sampleIndex, tStart, ignore, anyHit)) {
+        float c[3];
+        sample_colour(pc, ps, c);
+        blend_sample(pc, sample, c, frameColor);
         sample++;
-        if (sample == samplesPerFrame) {
-          if (samplesPerFrame == 25 && L.kernelMode == 0) {  // clamp only in linearKernel (:318-320)
-#pragma unroll
-            for (int k = 0; k < 3; k++) frameColor[k] = fminf(fmaxf(frameColor[k], 0.0f), 1.0f);
-          }
+        if (sample == pc.samplesPerFrame) {
+          finish_frame_colour(pc, L.kernelMode, frameColor);
           sink.frame(L, L.cam.frameCount + (unsigned)frame * L.frameStride, frameColor);
           sample = 0;
           frame++;
@@ -739,18 +136,19 @@ __global__ void __launch_bounds__(LT_BLOCK) k_path(LtSceneDev sc, LtLaunch L, fl
           }
         }
         unsigned fcNext = L.cam.frameCount + (unsigned)frame * L.frameStride;
-        sampleIndex = (samplesPerFrame == 25) ? fcNext * 32u + (unsigned)sample : fcNext;
-        direct[0] = direct[1] = direct[2] = 0.0f;
-        indirect[0] = indirect[1] = indirect[2] = 0.0f;
-        stage = ST_PRIMARY;
+        sampleIndex = (pc.samplesPerFrame == 25) ? fcNext * 32u + (unsigned)sample : fcNext;
+        path_reset(ps);
         t.r = cameraRay;
+        ignore = -1;
+        tStart = pc.tInit;
+        anyHit = false;
       }
       trav_begin<STATS>(t, sc, ignore, tStart, anyHit, cnt);
       traversing = (t.cur != LT_DONE);
     }
     if (!__any_sync(0xffffffffu, alive)) break;
 
-    // ---------------- phase T: resumable while-while traversal ----------------
+    // ---------------- phase T: resumable traversal ----------------
     while (true) {
       unsigned active = __ballot_sync(0xffffffffu, traversing);
       if (active == 0u) break;
@@ -758,7 +156,7 @@ __global__ void __launch_bounds__(LT_BLOCK) k_path(LtSceneDev sc, LtLaunch L, fl
       if (waiting && __popc(active) < L.refillThreshold) break;
       if (traversing) {
         int n = trav_collect<STATS>(t, sc, stk, list, t.anyHit ? L.batchAnyHit : L.batchClosest, cnt);
-        trav_test<STATS>(t, sc, list, n, epsThr, cnt);
+        trav_test<STATS>(t, sc, list, n, pc.epsThr, cnt);
         traversing = (t.cur != LT_DONE);
       }
     }

@@ -1,0 +1,390 @@
+// lt_wavefront.cu -- wavefront form of the stochastic pipelines (basic_lighting / accumulator /
+// global_illumination): the same per-path arithmetic as k_path (lt_kernels.cu), reorganised so that
+// every kernel does one kind of work for every ray that needs it.
+//
+//   generate   camera ray of every (pixel, frame) path of the batch        -> ray queue
+//   trace      persistent warps pull rays from the queue; a lane that finishes its ray pulls the
+//              next one at once, so lanes never wait for the longest ray of their warp
+//   shade      one thread per finished ray: consume the hit (shade_step), append the next ray of the
+//              path to the other queue or deposit the finished sample
+//   (trace, shade) x (2 + 2*maxRayDepth) rounds, no host synchronisation: queue sizes stay on the device
+//   accumulate per pixel, frames of the batch in order: running mean / weighted sum / store
+//
+// In a round all rays are of one kind (all primary, all shadow, all extension), shading code runs on
+// dense arrays, and the running mean is applied in frame order, so results are bit-identical to
+// k_path's.  Path state lives in HBM (64 B/path) between rounds.
+#include "lt_device.cuh"
+
+#define WF_BLOCK LT_BLOCK
+#define WF_CHUNK 256  // queue entries a warp claims per global atomic
+
+struct LtWfBuffers {
+  float4* stA;        // nrm.xyz, extW
+  float4* stB;        // diffuse.rgb, bits(hitPrim)
+  float4* stC;        // direct.rgb, bits(depth | stage << 8)
+  float4* stD;        // indirect.rgb, -
+  float4* frameCol;   // running frame colour of the path (the 25-sample blend, or the single sample)
+  float4* rayO[2];    // origin.xyz, tStart
+  float4* rayD[2];    // direction.xyz, bits((ignore + 1) | anyHit << 31)
+  int* rayPath[2];    // path id of the queue entry
+  float4* hits;       // t, u, v, bits(prim | hit << 31), indexed like the current queue
+  int* counts;        // [0],[1] queue sizes, [2] trace work counter
+};
+
+__device__ __forceinline__ void pixel_of_path(long long path, int pixels, int width, int& px, int& py, int& frameLocal) {
+  frameLocal = (int)(path / pixels);
+  int pixel = (int)(path - (long long)frameLocal * pixels);
+  py = pixel / width;
+  px = pixel - py * width;
+}
+
+__device__ __forceinline__ unsigned sample_index_of(const LtLaunch& L, const PathConsts& pc, int frame, int sample) {
+  unsigned fc = L.cam.frameCount + (unsigned)frame * L.frameStride;
+  return pc.samplesPerFrame == 25 ? fc * 32u + (unsigned)sample : fc;
+}
+
+// camera rays of all paths of the batch -> queue 0 (entry index = path index)
+__global__ void __launch_bounds__(WF_BLOCK) k_wf_generate(LtLaunch L, LtWfBuffers B, long long nPaths, int pixels) {
+  const PathConsts pc = path_consts(L);
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < nPaths;
+       p += (long long)gridDim.x * blockDim.x) {
+    int px, py, fl;
+    pixel_of_path(p, pixels, L.width, px, py, fl);
+    float fx, fy;
+    Ray r = camera_ray(L.cam, px, py, L.width, L.height, fx, fy);
+    B.rayO[0][p] = make_float4(r.ox, r.oy, r.oz, pc.tInit);
+    B.rayD[0][p] = make_float4(r.dx, r.dy, r.dz, __int_as_float(0));  // ignore = -1, closest hit
+    B.rayPath[0][p] = (int)p;
+    B.stC[p] = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(ST_PRIMARY << 8));
+    B.stD[p] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    B.counts[0] = (int)nPaths;
+    B.counts[1] = 0;
+    B.counts[2] = 0;
+  }
+}
+
+// Round 0 fused: camera ray -> trace -> shade for every path of the batch.  Primary rays are coherent
+// (neighbouring pixels), so one ray per thread is efficient here, and no ray/hit record of the primary
+// round ever touches memory; paths that end at once (miss, light hit) only deposit their colour.
+template <bool STATS>
+__global__ void __launch_bounds__(WF_BLOCK) k_wf_primary(LtSceneDev sc, LtLaunch L, LtWfBuffers B, long long nPaths,
+                                                         int pixels, int sample, LtCounters* gcnt) {
+  extern __shared__ int smemStack[];
+  int* stk = smemStack + threadIdx.x;
+  int* list = smemStack + max(sc.stackDepth, 1) * LT_BLOCK + threadIdx.x;
+  const PathConsts pc = path_consts(L);
+  const unsigned lane = threadIdx.x & 31u;
+  LtCounters cnt = {0, 0, 0};
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long rounds = (nPaths + stride - 1) / stride;
+  for (long long it = 0; it < rounds; it++) {
+    long long p = it * stride + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    bool emit = false;
+    Trav t;
+    float tStart = 0.0f;
+    int ignore = -1;
+    bool anyHit = false;
+    if (p < nPaths) {
+      int px, py, fl;
+      pixel_of_path(p, pixels, L.width, px, py, fl);
+      float fx, fy;
+      t.r = camera_ray(L.cam, px, py, L.width, L.height, fx, fy);
+      trace<STATS>(t, sc, -1, pc.tInit, pc.epsThr, false, stk, list, cnt);
+      PathState ps;
+      ps.nrm[0] = ps.nrm[1] = ps.nrm[2] = 0.0f;
+      ps.diffuse[0] = ps.diffuse[1] = ps.diffuse[2] = 0.0f;
+      ps.extW = 0.0f;
+      ps.hitPrim = 0;
+      ps.depth = 0;
+      path_reset(ps);
+      const Hit h = t.h;
+      bool done = shade_step(sc, pc, ps, t.r, h, fx, fy, sample_index_of(L, pc, fl, sample), tStart, ignore, anyHit);
+      if (done) {
+        float col[3], fc[3] = {0.0f, 0.0f, 0.0f};
+        sample_colour(pc, ps, col);
+        if (sample > 0) {
+          float4 prev = B.frameCol[p];
+          fc[0] = prev.x; fc[1] = prev.y; fc[2] = prev.z;
+        }
+        blend_sample(pc, sample, col, fc);
+        B.frameCol[p] = make_float4(fc[0], fc[1], fc[2], 0.0f);
+      } else {
+        emit = true;
+        B.stA[p] = make_float4(ps.nrm[0], ps.nrm[1], ps.nrm[2], ps.extW);
+        B.stB[p] = make_float4(ps.diffuse[0], ps.diffuse[1], ps.diffuse[2], __int_as_float(ps.hitPrim));
+        B.stC[p] = make_float4(ps.direct[0], ps.direct[1], ps.direct[2],
+                               __int_as_float((ps.depth & 0xff) | (ps.stage << 8)));
+        B.stD[p] = make_float4(ps.indirect[0], ps.indirect[1], ps.indirect[2], 0.0f);
+      }
+    }
+    unsigned em = __ballot_sync(0xffffffffu, emit);
+    if (em != 0u) {
+      int base = 0;
+      int leader = __ffs(em) - 1;
+      if ((int)lane == leader) base = atomicAdd(&B.counts[0], __popc(em));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (emit) {
+        int slot = base + __popc(em & ((1u << lane) - 1u));
+        B.rayO[0][slot] = make_float4(t.r.ox, t.r.oy, t.r.oz, tStart);
+        B.rayD[0][slot] = make_float4(t.r.dx, t.r.dy, t.r.dz,
+                                      __int_as_float((int)((unsigned)(ignore + 1) | (anyHit ? 0x80000000u : 0u))));
+        B.rayPath[0][slot] = (int)p;
+      }
+    }
+  }
+  if (STATS) flush_counters(gcnt, cnt);
+}
+
+// zero the queue counters before a batch
+__global__ void k_wf_reset(LtWfBuffers B) {
+  B.counts[0] = 0;
+  B.counts[1] = 0;
+  B.counts[2] = 0;
+}
+
+// persistent trace: lanes pull queue entries through one warp-aggregated atomic per refill
+template <bool STATS>
+__global__ void __launch_bounds__(WF_BLOCK) k_wf_trace(LtSceneDev sc, LtLaunch L, LtWfBuffers B, int q,
+                                                       LtCounters* gcnt) {
+  extern __shared__ int smemStack[];
+  int* stk = smemStack + threadIdx.x;
+  int* list = smemStack + max(sc.stackDepth, 1) * LT_BLOCK + threadIdx.x;
+  const int n = B.counts[q];
+  const float epsThr = lt_eps(L.kernel);
+  const unsigned lane = threadIdx.x & 31u;
+  LtCounters cnt = {0, 0, 0};
+  const float4* __restrict__ rayO = B.rayO[q];
+  const float4* __restrict__ rayD = B.rayD[q];
+  Trav t;
+  t.cur = LT_DONE;
+  int entry = -1;
+  // the warp takes queue entries in chunks (one global atomic per WF_CHUNK rays) and deals them to
+  // its lanes from warp-uniform registers
+  int chunkNext = 0, chunkEnd = 0;
+  bool exhausted = false;  // warp-uniform: the queue has no more entries
+  while (true) {
+    bool has = entry >= 0;
+    unsigned need = __ballot_sync(0xffffffffu, !has);
+    if (need != 0u && !exhausted) {
+      if (chunkNext >= chunkEnd) {
+        int base = 0;
+        if (lane == 0u) base = atomicAdd(&B.counts[2], WF_CHUNK);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        chunkNext = base;
+        chunkEnd = min(base + WF_CHUNK, n);
+        if (base >= n) exhausted = true;
+      }
+      if (!exhausted) {
+        int idx = chunkNext + __popc(need & ((1u << lane) - 1u));
+        chunkNext += __popc(need);
+        if (!has && idx < chunkEnd) {
+          float4 o = rayO[idx], d = rayD[idx];
+          t.r.ox = o.x; t.r.oy = o.y; t.r.oz = o.z;
+          t.r.dx = d.x; t.r.dy = d.y; t.r.dz = d.z;
+          unsigned bits = (unsigned)__float_as_int(d.w);
+          trav_begin<STATS>(t, sc, (int)(bits & 0x7fffffffu) - 1, o.w, (bits >> 31) != 0u, cnt);
+          entry = idx;
+          if (t.cur == LT_DONE) {  // missed the root box: finished already
+            B.hits[idx] = make_float4(t.h.t, 0.0f, 0.0f, __int_as_float(0));
+            entry = -1;
+          }
+        }
+      }
+    }
+    has = entry >= 0;
+    if (!__any_sync(0xffffffffu, has)) {
+      if (exhausted) break;
+      continue;  // every ray just fetched missed the root box: fetch again
+    }
+    if (has) {
+      if (trav_iter<STATS>(t, sc, stk, list, epsThr, L.iterNodeSteps, L.iterTriTests, cnt)) {
+        B.hits[entry] = make_float4(t.h.t, t.h.u, t.h.v,
+                                    __int_as_float((int)((unsigned)t.h.prim | (t.h.hit ? 0x80000000u : 0u))));
+        entry = -1;
+      }
+    }
+  }
+  if (STATS) flush_counters(gcnt, cnt);
+}
+
+// one thread per finished ray of queue q: shade, then append the path's next ray to queue 1-q
+__global__ void __launch_bounds__(WF_BLOCK) k_wf_shade(LtSceneDev sc, LtLaunch L, LtWfBuffers B, int q, int pixels,
+                                                       int frame0, int sample) {
+  const PathConsts pc = path_consts(L);
+  const int n = B.counts[q];
+  const unsigned lane = threadIdx.x & 31u;
+  const int rounds = (n + (int)(gridDim.x * blockDim.x) - 1) / (int)(gridDim.x * blockDim.x);
+  for (int it = 0; it < rounds; it++) {
+    int i = (it * (int)gridDim.x + (int)blockIdx.x) * (int)blockDim.x + (int)threadIdx.x;
+    bool valid = i < n;
+    bool emit = false;
+    Ray r = {0, 0, 0, 0, 0, 1};
+    float tStart = 0.0f;
+    int ignore = -1, path = 0;
+    bool anyHit = false;
+    if (valid) {
+      path = B.rayPath[q][i];
+      float4 o = B.rayO[q][i], d = B.rayD[q][i], hv = B.hits[i];
+      r.ox = o.x; r.oy = o.y; r.oz = o.z;
+      r.dx = d.x; r.dy = d.y; r.dz = d.z;
+      Hit h;
+      h.t = hv.x; h.u = hv.y; h.v = hv.z;
+      unsigned hb = (unsigned)__float_as_int(hv.w);
+      h.prim = (int)(hb & 0x7fffffffu);
+      h.hit = (int)(hb >> 31);
+      PathState ps;
+      float4 a = B.stA[path], b = B.stB[path], c = B.stC[path], dd = B.stD[path];
+      ps.nrm[0] = a.x; ps.nrm[1] = a.y; ps.nrm[2] = a.z; ps.extW = a.w;
+      ps.diffuse[0] = b.x; ps.diffuse[1] = b.y; ps.diffuse[2] = b.z; ps.hitPrim = __float_as_int(b.w);
+      ps.direct[0] = c.x; ps.direct[1] = c.y; ps.direct[2] = c.z;
+      int packed = __float_as_int(c.w);
+      ps.depth = packed & 0xff;
+      ps.stage = (packed >> 8) & 0xff;
+      ps.indirect[0] = dd.x; ps.indirect[1] = dd.y; ps.indirect[2] = dd.z;
+      int px, py, fl;
+      pixel_of_path(path, pixels, L.width, px, py, fl);
+      float fx = FADD(FDIV((float)px, (float)L.width), -0.5f);
+      float fy = FADD(FDIV((float)py, (float)L.height), -0.5f);
+      unsigned sampleIndex = sample_index_of(L, pc, frame0 + fl, sample);
+      bool done = shade_step(sc, pc, ps, r, h, fx, fy, sampleIndex, tStart, ignore, anyHit);
+      if (done) {
+        float col[3], fc[3];
+        sample_colour(pc, ps, col);
+        float4 prev = B.frameCol[path];
+        fc[0] = prev.x; fc[1] = prev.y; fc[2] = prev.z;
+        blend_sample(pc, sample, col, fc);
+        B.frameCol[path] = make_float4(fc[0], fc[1], fc[2], 0.0f);
+      } else {
+        emit = true;
+        B.stA[path] = make_float4(ps.nrm[0], ps.nrm[1], ps.nrm[2], ps.extW);
+        B.stB[path] = make_float4(ps.diffuse[0], ps.diffuse[1], ps.diffuse[2], __int_as_float(ps.hitPrim));
+        B.stC[path] = make_float4(ps.direct[0], ps.direct[1], ps.direct[2],
+                                  __int_as_float((ps.depth & 0xff) | (ps.stage << 8)));
+        B.stD[path] = make_float4(ps.indirect[0], ps.indirect[1], ps.indirect[2], 0.0f);
+      }
+    }
+    // warp-aggregated append to the other queue
+    unsigned em = __ballot_sync(0xffffffffu, emit);
+    if (em != 0u) {
+      int base = 0;
+      int leader = __ffs(em) - 1;
+      if ((int)lane == leader) base = atomicAdd(&B.counts[1 - q], __popc(em));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (emit) {
+        int slot = base + __popc(em & ((1u << lane) - 1u));
+        B.rayO[1 - q][slot] = make_float4(r.ox, r.oy, r.oz, tStart);
+        B.rayD[1 - q][slot] = make_float4(r.dx, r.dy, r.dz,
+                                          __int_as_float((int)((unsigned)(ignore + 1) | (anyHit ? 0x80000000u : 0u))));
+        B.rayPath[1 - q][slot] = path;
+      }
+    }
+  }
+}
+
+// between rounds: the consumed queue becomes the next output queue
+__global__ void k_wf_swap(LtWfBuffers B, int q) {
+  B.counts[q] = 0;
+  B.counts[2] = 0;
+}
+
+// frames of the batch, in order, through the frame combiner (accumulator.frag:10-19)
+__global__ void __launch_bounds__(WF_BLOCK) k_wf_accumulate(LtLaunch L, LtWfBuffers B, float* __restrict__ out,
+                                                            int pixels, int frame0, int batchFrames) {
+  const PathConsts pc = path_consts(L);
+  int pixel = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pixel >= pixels) return;
+  long long id = (long long)pixel * L.depth;
+  FrameSink sink;  // a batch that starts at frame0 > 0 continues from what earlier batches wrote to `out`
+  if (frame0 == 0) sink.begin(L, out, id);
+  else {
+    sink.acc[0] = out[id + 0]; sink.acc[1] = out[id + 1]; sink.acc[2] = out[id + 2];
+  }
+  for (int f = 0; f < batchFrames; f++) {
+    float4 v = B.frameCol[(long long)f * pixels + pixel];
+    float c[3] = {v.x, v.y, v.z};
+    finish_frame_colour(pc, L.kernelMode, c);
+    sink.frame(L, L.cam.frameCount + (unsigned)(frame0 + f) * L.frameStride, c);
+  }
+  sink.end(out, id);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+size_t lt_wf_bytes_per_path() {
+  return sizeof(float4) * (4 + 1 + 2 * 2 + 1) + sizeof(int) * 2;  // state, frame colour, 2 queues, hits, path ids
+}
+
+size_t lt_wf_workspace_bytes(long long nPaths) { return lt_wf_bytes_per_path() * (size_t)nPaths + 256; }
+
+static LtWfBuffers carve(void* workspace, long long nPaths) {
+  LtWfBuffers B;
+  char* p = (char*)workspace;
+  auto take = [&](size_t bytes) {
+    char* r = p;
+    p += (bytes + 255) & ~(size_t)255;
+    return r;
+  };
+  B.counts = (int*)take(256);
+  size_t f4 = sizeof(float4) * (size_t)nPaths;
+  B.stA = (float4*)take(f4);
+  B.stB = (float4*)take(f4);
+  B.stC = (float4*)take(f4);
+  B.stD = (float4*)take(f4);
+  B.frameCol = (float4*)take(f4);
+  for (int k = 0; k < 2; k++) {
+    B.rayO[k] = (float4*)take(f4);
+    B.rayD[k] = (float4*)take(f4);
+    B.rayPath[k] = (int*)take(sizeof(int) * (size_t)nPaths);
+  }
+  B.hits = (float4*)take(f4);
+  return B;
+}
+
+size_t lt_wf_workspace_bytes_padded(long long nPaths) {
+  // carve() rounds every array up to 256 bytes
+  return lt_wf_workspace_bytes(nPaths) + 256 * 16;
+}
+
+int lt_launch_render_wavefront(const LtSceneDev& sc, const LtLaunch& L, float* dOut, LtCounters* dCounters,
+                               void* workspace, int batchFrames, int smCount, cudaStream_t stream) {
+  const int pixels = L.width * L.height;
+  const bool stats = (L.flags & 1) != 0;
+  const bool isGI = (L.kernel == 5 || L.kernel == 6);
+  const int samples = (L.kernel == 3 || L.kernel == 5) ? 25 : 1;
+  const int maxDepth = L.maxRayDepth > 0 ? L.maxRayDepth : 16;
+  const int rounds = isGI ? 2 + 2 * maxDepth : 2;
+  const size_t smem = (size_t)((sc.stackDepth < 1 ? 1 : sc.stackDepth) + LT_MAX_BATCH) * LT_BLOCK * sizeof(int);
+  const int persistentBlocks = smCount * 8;
+  int launches = 0;
+  for (int frame0 = 0; frame0 < L.frames; frame0 += batchFrames) {
+    int nf = L.frames - frame0 < batchFrames ? L.frames - frame0 : batchFrames;
+    long long nPaths = (long long)nf * pixels;
+    LtWfBuffers B = carve(workspace, (long long)batchFrames * pixels);
+    LtLaunch Lb = L;
+    Lb.cam.frameCount = L.cam.frameCount + (unsigned)frame0 * L.frameStride;  // frame index 0 of the batch
+    int grid = (int)((nPaths + WF_BLOCK - 1) / WF_BLOCK);
+    if (grid > smCount * 32) grid = smCount * 32;
+    for (int s = 0; s < samples; s++) {
+      // round 0 (primary rays) fused into one kernel; its survivors are queue 0
+      k_wf_reset<<<1, 1, 0, stream>>>(B);
+      if (stats) k_wf_primary<true><<<grid, WF_BLOCK, smem, stream>>>(sc, Lb, B, nPaths, pixels, s, dCounters);
+      else k_wf_primary<false><<<grid, WF_BLOCK, smem, stream>>>(sc, Lb, B, nPaths, pixels, s, nullptr);
+      launches += 2;
+      int q = 0;
+      for (int r = 1; r < rounds; r++) {
+        if (stats) k_wf_trace<true><<<persistentBlocks, WF_BLOCK, smem, stream>>>(sc, Lb, B, q, dCounters);
+        else k_wf_trace<false><<<persistentBlocks, WF_BLOCK, smem, stream>>>(sc, Lb, B, q, nullptr);
+        k_wf_shade<<<grid, WF_BLOCK, 0, stream>>>(sc, Lb, B, q, pixels, 0, s);
+        k_wf_swap<<<1, 1, 0, stream>>>(B, q);
+        launches += 3;
+        q = 1 - q;
+      }
+    }
+    k_wf_accumulate<<<(pixels + WF_BLOCK - 1) / WF_BLOCK, WF_BLOCK, 0, stream>>>(L, B, dOut, pixels, frame0, nf);
+    launches++;
+  }
+  return launches;
+}

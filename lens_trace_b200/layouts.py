@@ -34,6 +34,8 @@ ACCUM_WEIGHTED_SUM = 2
 
 FLAG_STATS = 1
 FLAG_CULL = 2
+FLAG_MEGAKERNEL = 4
+FLAG_WAVEFRONT = 8
 
 
 def make_camera(x, y, z, yaw=0.0, frame_count=0):

@@ -79,36 +79,44 @@ def test_reference_known_answer_on_gpu(ctx):
         assert flat[x] == 0.0 and flat[x + 1] == 1.0 and flat[x + 2] == 0.0
 
 
+PIPES = [L.FLAG_MEGAKERNEL, L.FLAG_WAVEFRONT]  # the two schedules of the stochastic kernels: identical output
+
+
+@pytest.mark.parametrize("pipe", PIPES)
 @pytest.mark.parametrize("kernel,depth", [(L.KERNEL_ACCUMULATOR, 0), (L.KERNEL_GI, 4), (L.KERNEL_GI, 16),
                                           (L.KERNEL_GI, 1)])
 @pytest.mark.parametrize("name", ["cornell_box", "cornell_box_lens", "single_light"])
 @pytest.mark.parametrize("frame", [0, 1, 7, 63])
-def test_stochastic_single_sample(ctx, kernel, depth, name, frame):
+def test_stochastic_single_sample(ctx, pipe, kernel, depth, name, frame):
     sb, sc = gpu_scene(ctx, name)
     cam = util.default_camera(0.0, frame)
     w, h = 128, 96
-    got = ctx.render(sc, cam, capi.make_params(kernel, w, h, max_ray_depth=depth))
+    got = ctx.render(sc, cam, capi.make_params(kernel, w, h, max_ray_depth=depth, flags=pipe))
     want = O.render(kernel, sb, cam, w, h, max_ray_depth=depth if depth else 16, threads=0)
     assert np.isfinite(got).all()
     assert_images_match(got, want, "kernel %d frame %d" % (kernel, frame), max_outliers=3)
 
 
+@pytest.mark.parametrize("pipe", PIPES)
 @pytest.mark.parametrize("kernel", [L.KERNEL_LIGHTING25, L.KERNEL_GI25])
 @pytest.mark.parametrize("mode", [0, 1])
-def test_blend25_kernels(ctx, kernel, mode):
+def test_blend25_kernels(ctx, pipe, kernel, mode):
     sb, sc = gpu_scene(ctx, "cornell_box")
     cam = util.default_camera(0.05, 2)
-    got = ctx.render(sc, cam, capi.make_params(kernel, 64, 48, kernel_mode=mode, max_ray_depth=3))
+    got = ctx.render(sc, cam, capi.make_params(kernel, 64, 48, kernel_mode=mode, max_ray_depth=3, flags=pipe))
     want = O.render(kernel, sb, cam, 64, 48, kernel_mode=mode, max_ray_depth=3, threads=0)
     assert_images_match(got, want, "blend25 kernel %d" % kernel, max_outliers=3)
 
 
-def test_running_mean_matches_frame_by_frame_protocol(ctx):
+@pytest.mark.parametrize("pipe", PIPES)
+def test_running_mean_matches_frame_by_frame_protocol(ctx, pipe):
     """examples/global_illumination/src/main.cpp:296-325: one sample per frame, frameCount = 0,1,2..,
     running mean.  One multi-frame launch == the oracle rendering frame by frame and accumulating."""
     sb, sc = gpu_scene(ctx, "cornell_box")
     w, h, frames = 96, 64, 6
-    p = capi.make_params(L.KERNEL_GI, w, h, max_ray_depth=4, frames=frames, accum_mode=L.ACCUM_RUNNING_MEAN)
+    p = capi.make_params(L.KERNEL_GI, w, h, max_ray_depth=4, frames=frames, accum_mode=L.ACCUM_RUNNING_MEAN,
+                         flags=pipe)
+    ctx.accum_reset()
     got = ctx.render(sc, util.default_camera(0.0, 0), p)
     acc = np.zeros((h, w, 3), np.float32)
     for f in range(frames):
@@ -117,7 +125,8 @@ def test_running_mean_matches_frame_by_frame_protocol(ctx):
     # the same through successive single-frame calls sharing the context accumulator
     ctx.accum_reset()
     for f in range(frames):
-        p1 = capi.make_params(L.KERNEL_GI, w, h, max_ray_depth=4, frames=1, accum_mode=L.ACCUM_RUNNING_MEAN)
+        p1 = capi.make_params(L.KERNEL_GI, w, h, max_ray_depth=4, frames=1, accum_mode=L.ACCUM_RUNNING_MEAN,
+                              flags=pipe)
         step = ctx.render(sc, util.default_camera(0.0, f), p1)
     util.assert_bit_equal(step, got, "multi-frame launch vs frame-by-frame launches")
 
@@ -136,6 +145,20 @@ def test_accumulating_a_deterministic_kernel(ctx):
     np.testing.assert_allclose(got, one, rtol=1e-6, atol=1e-7)
 
 
+def test_wavefront_batches_equal_one_batch(ctx, monkeypatch):
+    """frames split over several wavefront batches (workspace cap) == megakernel, bit for bit"""
+    sb, sc = gpu_scene(ctx, "cornell_box")
+    w, h, frames = 64, 48, 7
+    cam = util.default_camera(0.0, 3)
+    ctx.accum_reset()
+    a = ctx.render(sc, cam, capi.make_params(L.KERNEL_GI, w, h, max_ray_depth=3, frames=frames,
+                                             accum_mode=L.ACCUM_RUNNING_MEAN, flags=L.FLAG_MEGAKERNEL))
+    ctx.accum_reset()
+    b = ctx.render(sc, cam, capi.make_params(L.KERNEL_GI, w, h, max_ray_depth=3, frames=frames,
+                                             accum_mode=L.ACCUM_RUNNING_MEAN, flags=L.FLAG_WAVEFRONT))
+    util.assert_bit_equal(a, b, "wavefront vs megakernel")
+
+
 def test_weighted_sum_split_equals_mean(ctx):
     # sample split across G "ranks": rank g renders frames g, g+G, .. weighted 1/N; the sum is the mean
     sb, sc = gpu_scene(ctx, "cornell_box")
@@ -152,12 +175,13 @@ def test_weighted_sum_split_equals_mean(ctx):
     np.testing.assert_allclose(total, mean, rtol=1e-5, atol=1e-6)
 
 
-def test_stats_count_the_reference_traversal(ctx):
+@pytest.mark.parametrize("pipe", PIPES)
+def test_stats_count_the_reference_traversal(ctx, pipe):
     for name, kernel, depth in (("cornell_box", L.KERNEL_BASIC_CU, 0), ("cornell_box_lens", L.KERNEL_BASIC_CU, 0),
                                 ("cornell_box", L.KERNEL_GI, 4), ("multi_leaf", L.KERNEL_BASIC_CU, 0)):
         sb, sc = gpu_scene(ctx, name)
         cam = util.default_camera(0.0, 1)
-        ctx.render(sc, cam, capi.make_params(kernel, 96, 96, max_ray_depth=depth, flags=L.FLAG_STATS))
+        ctx.render(sc, cam, capi.make_params(kernel, 96, 96, max_ray_depth=depth, flags=L.FLAG_STATS | pipe))
         st = ctx.stats()
         _, ost = O.render(kernel, sb, cam, 96, 96, max_ray_depth=depth if depth else 16, with_stats=True, threads=0)
         assert (st.rays, st.node_tests, st.tri_tests) == (ost.rays, ost.nodeTests, ost.triTests), name
