@@ -318,8 +318,9 @@ def main():
         pk = peaks()
         sm_count = st.sm_count or 148
         fp32_peak = sm_count * 128 * pk["sm_max_mhz"] * 1e6  # lane-instructions / s
-        alg_instr = 12.0 * node_tests + 45.0 * tri_tests
-        alg_bytes = 32.0 * node_tests + 36.0 * tri_tests
+        # roofline of ONE GPU's kernels: the counters were summed over ranks
+        alg_instr = (12.0 * node_tests + 45.0 * tri_tests) / world
+        alg_bytes = (32.0 * node_tests + 36.0 * tri_tests) / world
         k_s = kernel_ms / args.steps * 1e-3
         scene_bytes = sb.nodes.nbytes + sb.prims.nbytes
         level = "hbm" if scene_bytes > 126e6 else ("l2" if scene_bytes > 200e3 else "l1")

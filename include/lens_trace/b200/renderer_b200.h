@@ -26,6 +26,7 @@ private:
   lt_ctx* ctx;
   std::map<SceneKey, lt_scene*> sceneCache;
   std::map<std::string, int> kernelCache;
+  std::map<std::string, int> pluginCache;  // user .cu kernels compiled for this context
 
 public:
   RendererB200();

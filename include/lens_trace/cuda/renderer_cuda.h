@@ -7,11 +7,14 @@
 
 class RendererCUDA final : public Renderer {
 private:
-  RendererB200 impl;
+  RendererB200* impl;  // behind a pointer: the class layout stays fixed for compiled applications
 
 public:
   RendererCUDA();
   ~RendererCUDA();
+
+  RendererCUDA(const RendererCUDA&) = delete;
+  RendererCUDA& operator=(const RendererCUDA&) = delete;
 
   void render(void* pRenderProperties);
 };

@@ -9,11 +9,14 @@
 
 class RendererOpenCL final : public Renderer {
 private:
-  RendererB200 impl;
+  RendererB200* impl;  // behind a pointer: the class layout stays fixed for compiled applications
 
 public:
   RendererOpenCL();
   ~RendererOpenCL();
+
+  RendererOpenCL(const RendererOpenCL&) = delete;
+  RendererOpenCL& operator=(const RendererOpenCL&) = delete;
 
   void render(void* pRenderProperties);
 };

@@ -140,6 +140,16 @@ int lt_last_stats(const lt_ctx* ctx, lt_stats* out_stats);
 int lt_debug_random(lt_ctx* ctx, const float* fx, const float* fy, const float* seed, int n, float* out);
 int lt_debug_hemisphere(lt_ctx* ctx, const float* u1, const float* u2, const float* up3, int n, float* out4);
 
+/* --- plug-in kernels: a user-written .cu file with the reference's kernel ABI (extern "C" __global__
+ * linearKernel / tileKernel(LinearBVHNode*, Primitive*, Material*, LightContainer*, Camera*, float* out,
+ * int width, int height, int depth), resources/kernels/cuda/basic.cu:331-340).  Replaces the NVRTC compile
+ * and launch of src/cuda/renderer_cuda.cpp:20-39,57-88,113-133 for files that are not one of the shipped
+ * kernels: compiled once per context for sm_100a, then launched on the scene's buffers in the reference
+ * layouts with the reference's launch shape (block_x x block_y threads, 32x1 when 0). --- */
+int lt_plugin_load(lt_ctx* ctx, const char* kernel_file_path, int* out_plugin_id);
+int lt_render_plugin(lt_ctx* ctx, lt_scene* scene, const void* camera28, int plugin_id, int kernel_mode, int width,
+                     int height, int depth, int block_x, int block_y, float* host_out);
+
 /* Maps RenderProperties*::kernelFilePath to an lt_kernel by the file's base name and, when the file
  * is readable, its defining text (SAMPLE_COUNT, epsilon); returns LT_ERR_UNSUPPORTED for a file that
  * is not one of the shipped kernels. */

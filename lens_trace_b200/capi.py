@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "liblt_b200.so")
 SYMBOLS = [
     "lt_api_version", "lt_ctx_create", "lt_ctx_destroy", "lt_last_error", "lt_ctx_set_stream", "lt_scene_upload",
     "lt_scene_release", "lt_render", "lt_render_device", "lt_accum_reset", "lt_accum_read", "lt_primary_hits",
-    "lt_last_stats", "lt_kernel_from_path", "lt_kernel_name", "lt_debug_random", "lt_debug_hemisphere",
+    "lt_last_stats", "lt_kernel_from_path", "lt_kernel_name", "lt_debug_random", "lt_debug_hemisphere", "lt_plugin_load", "lt_render_plugin",
 ]
 
 
@@ -72,6 +72,9 @@ def load():
     lib.lt_last_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
     lib.lt_debug_random.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     lib.lt_debug_hemisphere.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    lib.lt_plugin_load.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_int)]
+    lib.lt_render_plugin.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     C.c_int, C.c_int, C.c_void_p]
     lib.lt_kernel_from_path.argtypes = [C.c_char_p]
     lib.lt_kernel_name.argtypes = [C.c_int]
     lib.lt_kernel_name.restype = C.c_char_p
@@ -164,6 +167,18 @@ class Context:
         self._check(self.lib.lt_primary_hits(self.h, scene.h, cam.ctypes.data, kernel, width, height, ids.ctypes.data,
                                              hit.ctypes.data, tuv.ctypes.data), "lt_primary_hits")
         return ids, hit, tuv
+
+    def plugin_load(self, path):
+        pid = C.c_int(-1)
+        self._check(self.lib.lt_plugin_load(self.h, path.encode(), C.byref(pid)), "lt_plugin_load")
+        return pid.value
+
+    def render_plugin(self, scene, camera, plugin_id, width, height, depth=3, kernel_mode=0, block=(0, 0)):
+        out = np.zeros((height, width, depth), dtype=np.float32)
+        cam = np.ascontiguousarray(camera, dtype=L.CAMERA)
+        self._check(self.lib.lt_render_plugin(self.h, scene.h, cam.ctypes.data, plugin_id, kernel_mode, width, height,
+                                              depth, block[0], block[1], out.ctypes.data), "lt_render_plugin")
+        return out
 
     def debug_random(self, fx, fy, seed):
         fx, fy, seed = (np.ascontiguousarray(a, dtype=np.float32) for a in (fx, fy, seed))

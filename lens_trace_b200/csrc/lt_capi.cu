@@ -20,6 +20,8 @@ struct lt_ctx {
   float* dOut = nullptr;  // context-owned output / accumulator
   size_t outFloats = 0;
   LtCounters* dCounters = nullptr;
+  std::vector<LtPlugin*> plugins;  // compiled user kernels, by id
+  RefCamera* dCamera = nullptr;    // camera buffer for plug-in launches
   void* wfWorkspace = nullptr;  // wavefront path state / ray queues
   size_t wfBytes = 0;
   size_t totalMem = 0;
@@ -99,6 +101,8 @@ extern "C" void lt_ctx_destroy(lt_ctx* ctx) {
   if (ctx->dOut) cudaFree(ctx->dOut);
   if (ctx->dCounters) cudaFree(ctx->dCounters);
   if (ctx->wfWorkspace) cudaFree(ctx->wfWorkspace);
+  if (ctx->dCamera) cudaFree(ctx->dCamera);
+  for (LtPlugin* p : ctx->plugins) lt_plugin_free(p);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->ownStream) cudaStreamDestroy(ctx->ownStream);
@@ -405,6 +409,44 @@ extern "C" int lt_render(lt_ctx* ctx, lt_scene* scene, const void* camera28, con
   if (rc != LT_OK) return rc;
   rc = render_common(ctx, scene, L, ctx->dOut, true);
   if (rc != LT_OK) return rc;
+  if (host_out) CK(cudaMemcpy(host_out, ctx->dOut, floats * sizeof(float), cudaMemcpyDeviceToHost));
+  return LT_OK;
+}
+
+extern "C" int lt_plugin_load(lt_ctx* ctx, const char* kernel_file_path, int* out_plugin_id) {
+  if (!ctx || !kernel_file_path || !out_plugin_id) return fail(ctx, LT_ERR_INVALID, "lt_plugin_load: NULL argument");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaFree(0));  // make sure the primary context is current for the driver-API module load
+  std::string err;
+  LtPlugin* p = lt_plugin_compile(kernel_file_path, &err);
+  if (!p) return fail(ctx, LT_ERR_UNSUPPORTED, "lt_plugin_load: " + err);
+  ctx->plugins.push_back(p);
+  *out_plugin_id = (int)ctx->plugins.size() - 1;
+  return LT_OK;
+}
+
+extern "C" int lt_render_plugin(lt_ctx* ctx, lt_scene* scene, const void* camera28, int plugin_id, int kernel_mode,
+                                int width, int height, int depth, int block_x, int block_y, float* host_out) {
+  if (!ctx) return fail(nullptr, LT_ERR_INVALID, "lt_render_plugin: ctx is NULL");
+  if (!scene || !camera28 || plugin_id < 0 || plugin_id >= (int)ctx->plugins.size() || width <= 0 || height <= 0 ||
+      depth < 1)
+    return fail(ctx, LT_ERR_INVALID, "lt_render_plugin: bad argument");
+  CK(cudaSetDevice(ctx->device));
+  size_t floats = (size_t)width * height * depth;
+  int rc = ensure_out(ctx, floats);
+  if (rc != LT_OK) return rc;
+  if (!ctx->dCamera) CK(cudaMalloc(&ctx->dCamera, sizeof(RefCamera)));
+  CK(cudaMemcpyAsync(ctx->dCamera, camera28, sizeof(RefCamera), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  std::string err;
+  if (lt_plugin_launch(ctx->plugins[plugin_id], kernel_mode ? 1 : 0, scene->dNodes, scene->dPrims, scene->dMats,
+                       scene->dLights, ctx->dCamera, ctx->dOut, width, height, depth, block_x, block_y, ctx->stream,
+                       &err) != 0)
+    return fail(ctx, LT_ERR_CUDA, "lt_render_plugin: " + err);
+  CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaEventElapsedTime(&ctx->stats.kernel_ms, ctx->ev0, ctx->ev1));
+  ctx->stats.kernel_launches = 1;
   if (host_out) CK(cudaMemcpy(host_out, ctx->dOut, floats * sizeof(float), cudaMemcpyDeviceToHost));
   return LT_OK;
 }

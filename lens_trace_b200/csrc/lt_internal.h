@@ -119,3 +119,12 @@ int lt_launch_debug_hemisphere(const float* u1, const float* u2, const float* up
 size_t lt_wf_workspace_bytes_padded(long long nPaths);
 int lt_launch_render_wavefront(const LtSceneDev& sc, const LtLaunch& L, float* dOut, LtCounters* dCounters,
                                void* workspace, int batchFrames, int smCount, cudaStream_t stream);
+
+// user-written CUDA kernels with the reference's plug-in ABI (lt_plugin.cu)
+#include <string>
+struct LtPlugin;
+LtPlugin* lt_plugin_compile(const char* path, std::string* err);
+void lt_plugin_free(LtPlugin* p);
+int lt_plugin_launch(LtPlugin* p, int kernelMode, const void* dNodes, const void* dPrims, const void* dMats,
+                     const void* dLights, const void* dCamera, float* dOut, int width, int height, int depth, int bx,
+                     int by, cudaStream_t stream, std::string* err);

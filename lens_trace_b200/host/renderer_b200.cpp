@@ -53,10 +53,27 @@ void RendererB200::renderCommon(const std::string& kernelFilePath, KernelMode ke
     kernel = lt_kernel_from_path(resolved == "INVALID RESOURCE" ? kernelFilePath.c_str() : resolved.c_str());
     kernelCache[kernelFilePath] = kernel;
   }
+  // not one of the shipped kernels: a user-written .cu with the reference's kernel ABI is compiled
+  // (once) with NVRTC for sm_100a and launched like the reference launches it; anything else is an error
+  int plugin = -1;
   if (kernel < 0) {
-    printf("Kernel Error: '%s' is not a kernel this renderer provides (%s)\n", kernelFilePath.c_str(),
-           lt_last_error(nullptr));
-    return;
+    std::string resolved = Resource::findResource(kernelFilePath);
+    bool isCu = resolved.size() > 3 && resolved.compare(resolved.size() - 3, 3, ".cu") == 0;
+    std::map<std::string, int>::iterator pc = pluginCache.find(kernelFilePath);
+    if (pc != pluginCache.end()) {
+      plugin = pc->second;
+    } else if (isCu) {
+      if (lt_plugin_load(ctx, resolved.c_str(), &plugin) != LT_OK) {
+        printf("%s\n", lt_last_error(ctx));
+        plugin = -1;
+      }
+      pluginCache[kernelFilePath] = plugin;
+    }
+    if (plugin < 0) {
+      printf("Kernel Error: '%s' is not a kernel this renderer provides (%s)\n", kernelFilePath.c_str(),
+             isCu ? "plug-in compilation failed" : "only the shipped kernels and CUDA plug-ins are supported");
+      return;
+    }
   }
 
   SceneKey key;
@@ -115,7 +132,10 @@ void RendererB200::renderCommon(const std::string& kernelFilePath, KernelMode ke
            (unsigned long long)need);
     return;
   }
-  int rc = lt_render(ctx, scene, camera->getCameraBuffer(), &params, (float*)pOutputBuffer);
+  int rc = plugin >= 0
+               ? lt_render_plugin(ctx, scene, camera->getCameraBuffer(), plugin, params.kernel_mode, params.width,
+                                  params.height, params.depth, params.block_x, params.block_y, (float*)pOutputBuffer)
+               : lt_render(ctx, scene, camera->getCameraBuffer(), &params, (float*)pOutputBuffer);
   if (rc != LT_OK) {
     printf("Kernel Error: %d (%s)\n", rc, lt_last_error(ctx));
     return;
@@ -130,8 +150,8 @@ void RendererB200::renderCommon(const std::string& kernelFilePath, KernelMode ke
   }
 }
 
-RendererCUDA::RendererCUDA() {}
-RendererCUDA::~RendererCUDA() {}
+RendererCUDA::RendererCUDA() : impl(new RendererB200()) {}
+RendererCUDA::~RendererCUDA() { delete impl; }
 
 void RendererCUDA::render(void* pRenderProperties) {
   RenderPropertiesCUDA* p = (RenderPropertiesCUDA*)pRenderProperties;
@@ -143,12 +163,12 @@ void RendererCUDA::render(void* pRenderProperties) {
     block[0] = p->threadOrganization.blockSize[0];
     block[1] = p->threadOrganization.blockSize[1];
   }
-  impl.renderCommon(p->kernelFilePath, p->kernelMode, block, p->imageDimensions, p->pOutputBuffer, p->outputBufferSize,
+  impl->renderCommon(p->kernelFilePath, p->kernelMode, block, p->imageDimensions, p->pOutputBuffer, p->outputBufferSize,
                     p->pAccelerationStructureExplicit, p->pModel, p->pCamera, p->pNext);
 }
 
-RendererOpenCL::RendererOpenCL() {}
-RendererOpenCL::~RendererOpenCL() {}
+RendererOpenCL::RendererOpenCL() : impl(new RendererB200()) {}
+RendererOpenCL::~RendererOpenCL() { delete impl; }
 
 void RendererOpenCL::render(void* pRenderProperties) {
   RenderPropertiesOpenCL* p = (RenderPropertiesOpenCL*)pRenderProperties;
@@ -162,6 +182,6 @@ void RendererOpenCL::render(void* pRenderProperties) {
   }
   // The reference splits the image into work blocks and drops the remainder
   // (src/opencl/renderer_opencl.cpp:90); the whole image is rendered here.
-  impl.renderCommon(p->kernelFilePath, p->kernelMode, block, p->imageDimensions, p->pOutputBuffer, p->outputBufferSize,
+  impl->renderCommon(p->kernelFilePath, p->kernelMode, block, p->imageDimensions, p->pOutputBuffer, p->outputBufferSize,
                     p->pAccelerationStructureExplicit, p->pModel, p->pCamera, p->pNext);
 }

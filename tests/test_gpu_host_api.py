@@ -140,3 +140,76 @@ def test_reference_example_binaries_run_unchanged(tmp_path):
     out = os.path.join(util.ROOT, "output.jpg.ppm")
     assert os.path.getsize(out) > 2048 * 2048 * 3
     os.remove(out)
+
+
+def _echo_expected(sb, cam_z, frame_count, w, h):
+    idx = np.arange(w, dtype=np.float32)[None, :].repeat(h, 0)
+    idy = np.arange(h, dtype=np.float32)[:, None].repeat(w, 1)
+    p = (np.arange(w * h) % 42).reshape(h, w)
+    want = np.zeros((h, w, 3), np.float32)
+    want[..., 0] = np.float32(cam_z) + idx + np.float32(frame_count)
+    want[..., 1] = sb.materials["diffuse"][sb.prims["mat"][p], 1] + sb.prims["b"][p, 0]
+    want[..., 2] = np.float32(sb.lights["count"][0]) + sb.nodes["max"][0, 1] + idy
+    return want
+
+
+def test_plugin_kernel_through_the_c_abi():
+    """A user-written .cu with the reference's kernel ABI: compiled by NVRTC for sm_100a, launched on the
+    uploaded buffers in the reference layouts, both entry points, default and custom block shapes."""
+    from lens_trace_b200 import capi
+    ctx = capi.Context(0)
+    sb = util.scene("cornell_box")
+    sc = ctx.upload(sb)
+    pid = ctx.plugin_load(os.path.join(util.ROOT, "tests", "plugins", "echo_buffers.cu"))
+    cam = util.default_camera(0.0, 5)
+    w, h = 101, 37
+    want = _echo_expected(sb, -50.0, 5, w, h)
+    for mode, block in ((0, (0, 0)), (1, (0, 0)), (0, (8, 8)), (1, (4, 4)), (0, (16, 2))):
+        got = ctx.render_plugin(sc, cam, pid, w, h, kernel_mode=mode, block=block)
+        util.assert_bit_equal(got, want, "plug-in mode %d block %s" % (mode, block))
+    with pytest.raises(capi.LtError) as e:
+        ctx.plugin_load(os.path.join(util.ROOT, "tests", "plugins", "broken.cu"))
+    assert "undefined_symbol" in str(e.value)
+    with pytest.raises(capi.LtError):
+        ctx.plugin_load("/nonexistent/kernel.cu")
+    sc.release()
+    ctx.close()
+
+
+def test_plugin_kernel_through_renderer_cuda(world):
+    """kernelFilePath naming a .cu that is not a shipped kernel goes to the plug-in path (custom_kernel surface)."""
+    os.chdir(util.ROOT)
+    cam = host.Camera(0, 2.5, -50, 0)
+    model = host.Model("resources/models/cornell_box.obj")
+    accel = host.AccelerationStructure(model)
+    r = host.Renderer(host.PLATFORM_CUDA)
+    got = r.render("tests/plugins/echo_buffers.cu", 64, 40, accel, model, cam, block=(8, 8))
+    util.assert_bit_equal(got, _echo_expected(accel.buffers(), -50.0, 0, 64, 40))
+    out = np.full((40, 64, 3), -1, np.float32)
+    r.render("tests/plugins/broken.cu", 64, 40, accel, model, cam, out=out)  # reported, buffer untouched
+    assert (out == -1).all()
+    r.close()
+    accel.close()
+    model.close()
+    cam.close()
+
+
+def test_reference_kernel_source_as_a_plugin():
+    """The reference's own basic.cu, run UNMODIFIED through the plug-in path (NVRTC for sm_100a), gives the
+    same picture as the built-in pipeline that replaces it."""
+    from lens_trace_b200 import capi
+    src = os.path.join(util.ROOT, "oracle", "_ref", "resources", "kernels", "cuda", "basic.cu")
+    if not os.path.exists(src):
+        pytest.skip("oracle/_ref not built")
+    ctx = capi.Context(0)
+    for name in ("cornell_box", "cornell_box_lens"):
+        sb = util.scene(name)
+        sc = ctx.upload(sb)
+        pid = ctx.plugin_load(src)
+        for yaw in (0.0, 0.04):
+            cam = util.default_camera(yaw)
+            a = ctx.render_plugin(sc, cam, pid, 200, 150, block=(8, 8))
+            b = ctx.render(sc, cam, capi.make_params(L.KERNEL_BASIC_CU, 200, 150))
+            util.assert_bit_equal(a, b, "%s yaw %g: reference source as plug-in vs built-in pipeline" % (name, yaw))
+        sc.release()
+    ctx.close()
