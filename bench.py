@@ -22,7 +22,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 import numpy as np
@@ -74,36 +73,49 @@ def peaks():
     return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0, "source": "fallback"}
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe): one
+    nvidia-smi process streaming a sample every 50 ms between start() and summary()."""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], False
+        self.index, self.proc = index, None
 
-    def run(self):
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in out.strip().split(",")]
-                if len(f) >= 6:
-                    self.samples.append(f)
-            except Exception:
-                pass
-            time.sleep(0.2)
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            time.sleep(0.15)  # let the first sample land before the timed region starts
+        except Exception:
+            self.proc = None
 
     def summary(self):
-        self.stop_flag = True
-        if not self.samples:
+        if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(float(s[0]) for s in self.samples)
+        time.sleep(0.06)
+        self.proc.terminate()
+        try:
+            out = self.proc.communicate(timeout=5)[0]
+        except Exception:
+            out = ""
+        samples = []
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) >= 6:
+                try:
+                    float(f[0])
+                    samples.append(f)
+                except ValueError:
+                    pass
+        if not samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi gave no samples"]}
+        sm = sorted(float(s[0]) for s in samples)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": float(samples[0][1]), "reasons": reasons,
                 "samples": len(sm)}
 
 
@@ -264,19 +276,25 @@ def main():
     torch.cuda.synchronize()
     events = []
     kernel_events = []
+    trace_ms_total, trace_launches = 0.0, 0
     for _ in range(args.steps):
         flush.fill_(1.0)  # L2 flush between timed iterations (untimed)
         e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         e0.record(stream)
         if world > 1:
             acc.zero_()
-        ctx.render_device(scene, cam, make_step_params(), acc.data_ptr(), sync=False)
+        # synchronous call: the library brackets every traversal launch with its own CUDA events on this
+        # stream and sums them (lt_stats.trace_ms) -- the live duration of the dominant kernels
+        ctx.render_device(scene, cam, make_step_params(), acc.data_ptr(), sync=True)
         e1.record(stream)
         if world > 1:
             dist.all_reduce(acc)
         e2.record(stream)
         events.append((e0, e2))
         kernel_events.append((e0, e1))
+        st_step = ctx.stats()
+        trace_ms_total += st_step.trace_ms
+        trace_launches += st_step.trace_launches
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -321,7 +339,9 @@ def main():
         # roofline of ONE GPU's kernels: the counters were summed over ranks
         alg_instr = (12.0 * node_tests + 45.0 * tri_tests) / world
         alg_bytes = (32.0 * node_tests + 36.0 * tri_tests) / world
-        k_s = kernel_ms / args.steps * 1e-3
+        # the dominant kernels are the traversal kernels; their summed duration per step, measured live
+        trace_s = trace_ms_total / args.steps * 1e-3
+        k_s = trace_s if trace_s > 0 else kernel_ms / args.steps * 1e-3
         scene_bytes = sb.nodes.nbytes + sb.prims.nbytes
         level = "hbm" if scene_bytes > 126e6 else ("l2" if scene_bytes > 200e3 else "l1")
         l1_peak = sm_count * 128 * pk["sm_max_mhz"] * 1e6 / 1e9  # GB/s, nominal 128 B/clk/SM
@@ -348,9 +368,17 @@ def main():
                 roof["traffic_source"] = tr["capture"]
         pipeline = "wavefront (k_wf_primary + (k_wf_trace, k_wf_shade) x rounds + k_wf_accumulate)" \
             if launches_per_step > 1 else ("k_path" if kernel >= 3 else "k_flat")
-        roof.update({"kernel": pipeline, "kernel_ms_per_launch": kernel_ms / args.steps,
+        roof.update({"kernel": "k_wf_primary + k_wf_trace (traversal kernels of the wavefront pipeline)"
+                     if launches_per_step > 1 else pipeline,
+                     "pipeline": pipeline,
+                     "traversal_ms_per_step": trace_ms_total / args.steps,
+                     "traversal_launches_per_step": trace_launches / args.steps,
+                     "traversal_avg_launch_ms": trace_ms_total / max(1, trace_launches),
+                     "traversal_share_of_step": trace_ms_total / max(1e-9, kernel_ms),
+                     "pipeline_ms_per_step": kernel_ms / args.steps,
                      "kernels_per_step": launches_per_step,
-                     "algorithmic_bytes_per_launch": alg_bytes, "algorithmic_fp32_instr_per_launch": alg_instr,
+                     "algorithmic_units": "per step (all traversal launches of one step), per GPU",
+                     "algorithmic_bytes_per_step": alg_bytes, "algorithmic_fp32_instr_per_step": alg_instr,
                      "node_tests_per_ray": node_tests / rays, "tri_tests_per_ray": tri_tests / rays,
                      "fp32_issue": fp32, "node_fetch": fetch,
                      "hbm_view": {"achieved": alg_bytes / k_s / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
@@ -373,7 +401,9 @@ def main():
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
-            per = max(1, min(frames, 8))
+            # bounded sample: about 10-30 s of CPU work on the box's cores (one frame first to size it)
+            _, _, t1, _ = cpu_oracle_rate(sb, kernel, w, h, depth, [0])
+            per = max(1, min(frames, int(15.0 / max(t1, 1e-3))))
             v, r, secs, cores = cpu_oracle_rate(sb, kernel, w, h, depth, list(range(per)))
             line["cpu_baseline"] = {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "port",
                                     "sample": "frames 0..%d of the %d at full %dx%d (%.1f s of CPU work)" % (

@@ -94,6 +94,9 @@ typedef struct lt_stats {
   float upload_ms;      /* device time of the last lt_scene_upload (H2D + re-flatten) */
   int32_t kernel_launches; /* kernels launched by the last lt_render* call */
   int32_t sm_count;
+  float trace_ms;       /* part of kernel_ms spent in the traversal kernels (k_wf_primary + k_wf_trace, or the
+                           whole megakernel), CUDA events around each launch; 0 when the call was not synchronous */
+  int32_t trace_launches;
 } lt_stats;
 
 /* --- context: replaces RendererCUDA::RendererCUDA() (src/cuda/renderer_cuda.cpp:10-14). --- */

@@ -37,7 +37,8 @@ class RenderParams(C.Structure):
 class Stats(C.Structure):
     _fields_ = [
         ("rays", C.c_uint64), ("node_tests", C.c_uint64), ("tri_tests", C.c_uint64), ("kernel_ms", C.c_float),
-        ("upload_ms", C.c_float), ("kernel_launches", C.c_int32), ("sm_count", C.c_int32),
+        ("upload_ms", C.c_float), ("kernel_launches", C.c_int32), ("sm_count", C.c_int32), ("trace_ms", C.c_float),
+        ("trace_launches", C.c_int32),
     ]
 
 

@@ -20,6 +20,7 @@ struct lt_ctx {
   float* dOut = nullptr;  // context-owned output / accumulator
   size_t outFloats = 0;
   LtCounters* dCounters = nullptr;
+  std::vector<cudaEvent_t> traceEvents;  // pairs of events around traversal launches (timed when synchronous)
   std::vector<LtPlugin*> plugins;  // compiled user kernels, by id
   RefCamera* dCamera = nullptr;    // camera buffer for plug-in launches
   void* wfWorkspace = nullptr;  // wavefront path state / ray queues
@@ -103,6 +104,7 @@ extern "C" void lt_ctx_destroy(lt_ctx* ctx) {
   if (ctx->wfWorkspace) cudaFree(ctx->wfWorkspace);
   if (ctx->dCamera) cudaFree(ctx->dCamera);
   for (LtPlugin* p : ctx->plugins) lt_plugin_free(p);
+  for (cudaEvent_t e : ctx->traceEvents) cudaEventDestroy(e);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->ownStream) cudaStreamDestroy(ctx->ownStream);
@@ -368,9 +370,18 @@ static int render_common(lt_ctx* ctx, lt_scene* scene, const LtLaunch& L, float*
       }
     }
   }
+  const int kMaxTracePairs = 2048;
+  int tracePairs = 0;
+  bool timeTrace = wavefront && (sync || stats);
+  if (timeTrace && ctx->traceEvents.empty()) {
+    ctx->traceEvents.resize(2 * kMaxTracePairs);
+    for (size_t i = 0; i < ctx->traceEvents.size(); i++) cudaEventCreate(&ctx->traceEvents[i]);
+  }
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
   int launches = wavefront ? lt_launch_render_wavefront(scene->dev, L, dOut, ctx->dCounters, ctx->wfWorkspace,
-                                                        batchFrames, ctx->stats.sm_count, ctx->stream)
+                                                        batchFrames, ctx->stats.sm_count, ctx->stream,
+                                                        timeTrace ? ctx->traceEvents.data() : nullptr, kMaxTracePairs,
+                                                        &tracePairs)
                            : lt_launch_render(scene->dev, L, dOut, ctx->dCounters, ctx->stream);
   CK(cudaGetLastError());
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
@@ -378,6 +389,16 @@ static int render_common(lt_ctx* ctx, lt_scene* scene, const LtLaunch& L, float*
   if (sync || stats) {
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaEventElapsedTime(&ctx->stats.kernel_ms, ctx->ev0, ctx->ev1));
+    ctx->stats.trace_ms = wavefront ? 0.0f : ctx->stats.kernel_ms;
+    ctx->stats.trace_launches = wavefront ? tracePairs : 1;
+    for (int i = 0; i < tracePairs; i++) {
+      float ms = 0.0f;
+      cudaEventElapsedTime(&ms, ctx->traceEvents[2 * i], ctx->traceEvents[2 * i + 1]);
+      ctx->stats.trace_ms += ms;
+    }
+  } else {
+    ctx->stats.trace_ms = 0.0f;
+    ctx->stats.trace_launches = 0;
   }
   if (stats) {
     LtCounters h;

@@ -117,8 +117,11 @@ int lt_launch_debug_hemisphere(const float* u1, const float* u2, const float* up
 
 // wavefront pipeline (lt_wavefront.cu)
 size_t lt_wf_workspace_bytes_padded(long long nPaths);
+// traceEvents: optional pool of 2*maxTraceLaunches events; when given, every traversal launch is bracketed by a
+// pair of events and *traceLaunches receives the number of pairs recorded
 int lt_launch_render_wavefront(const LtSceneDev& sc, const LtLaunch& L, float* dOut, LtCounters* dCounters,
-                               void* workspace, int batchFrames, int smCount, cudaStream_t stream);
+                               void* workspace, int batchFrames, int smCount, cudaStream_t stream,
+                               cudaEvent_t* traceEvents, int maxTraceLaunches, int* traceLaunches);
 
 // user-written CUDA kernels with the reference's plug-in ABI (lt_plugin.cu)
 #include <string>

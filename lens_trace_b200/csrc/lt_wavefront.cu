@@ -349,7 +349,13 @@ size_t lt_wf_workspace_bytes_padded(long long nPaths) {
 }
 
 int lt_launch_render_wavefront(const LtSceneDev& sc, const LtLaunch& L, float* dOut, LtCounters* dCounters,
-                               void* workspace, int batchFrames, int smCount, cudaStream_t stream) {
+                               void* workspace, int batchFrames, int smCount, cudaStream_t stream,
+                               cudaEvent_t* traceEvents, int maxTraceLaunches, int* traceLaunches) {
+  int pairs = 0;
+  auto mark = [&](int which) {  // which: 0 = before, 1 = after a traversal launch
+    if (traceEvents && pairs < maxTraceLaunches) cudaEventRecord(traceEvents[2 * pairs + which], stream);
+    if (which == 1 && traceEvents && pairs < maxTraceLaunches) pairs++;
+  };
   const int pixels = L.width * L.height;
   const bool stats = (L.flags & 1) != 0;
   const bool isGI = (L.kernel == 5 || L.kernel == 6);
@@ -370,13 +376,17 @@ int lt_launch_render_wavefront(const LtSceneDev& sc, const LtLaunch& L, float* d
     for (int s = 0; s < samples; s++) {
       // round 0 (primary rays) fused into one kernel; its survivors are queue 0
       k_wf_reset<<<1, 1, 0, stream>>>(B);
+      mark(0);
       if (stats) k_wf_primary<true><<<grid, WF_BLOCK, smem, stream>>>(sc, Lb, B, nPaths, pixels, s, dCounters);
       else k_wf_primary<false><<<grid, WF_BLOCK, smem, stream>>>(sc, Lb, B, nPaths, pixels, s, nullptr);
+      mark(1);
       launches += 2;
       int q = 0;
       for (int r = 1; r < rounds; r++) {
+        mark(0);
         if (stats) k_wf_trace<true><<<persistentBlocks, WF_BLOCK, smem, stream>>>(sc, Lb, B, q, dCounters);
         else k_wf_trace<false><<<persistentBlocks, WF_BLOCK, smem, stream>>>(sc, Lb, B, q, nullptr);
+        mark(1);
         k_wf_shade<<<grid, WF_BLOCK, 0, stream>>>(sc, Lb, B, q, pixels, 0, s);
         k_wf_swap<<<1, 1, 0, stream>>>(B, q);
         launches += 3;
@@ -386,5 +396,6 @@ int lt_launch_render_wavefront(const LtSceneDev& sc, const LtLaunch& L, float* d
     k_wf_accumulate<<<(pixels + WF_BLOCK - 1) / WF_BLOCK, WF_BLOCK, 0, stream>>>(L, B, dOut, pixels, frame0, nf);
     launches++;
   }
+  if (traceLaunches) *traceLaunches = pairs;
   return launches;
 }
