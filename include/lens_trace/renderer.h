@@ -1,10 +1,3 @@
-// renderer.h -- the drop-in boundary: one virtual render(void*) (reference: include/lens_trace/renderer.h:5-9).
+// renderer.h -- forwarder: the public surface is declared in lens_trace/api.h (see there).
 #pragma once
-#include <stddef.h>
-#include <stdint.h>
-
-class Renderer {
-protected:
-public:
-  virtual void render(void* pRenderProperties) = 0;
-};
+#include "lens_trace/api.h"

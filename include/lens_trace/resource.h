@@ -1,10 +1,3 @@
-// resource.h -- path lookup used for kernel and model files (reference: src/resource.cpp:3-16).
+// resource.h -- forwarder: the public surface is declared in lens_trace/api.h (see there).
 #pragma once
-#include <fstream>
-#include <string>
-
-class Resource {
-public:
-  // the path itself if it opens, else /usr/local/share/lens_trace/<path>, else "INVALID RESOURCE"
-  static std::string findResource(std::string resourcePath);
-};
+#include "lens_trace/api.h"

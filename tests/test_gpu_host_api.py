@@ -105,7 +105,7 @@ def test_scene_file_end_to_end():
     os.chdir(util.ROOT)
     out = np.zeros((2048, 2048, 3), np.float32)
     dims = (C.c_uint64 * 3)()
-    rc = host.load().lth_run_scene_file(b"resources/scenes/basic_cuda.scene", out.ctypes.data, out.nbytes, C.byref(dims))
+    rc = host.load().lth_run_scene_file(b"resources/scenes/cornell_basic_cuda.scene", out.ctypes.data, out.nbytes, C.byref(dims))
     assert rc == 0 and tuple(dims) == (2048, 2048, 3)
     want = O.render(L.KERNEL_BASIC_CU, util.scene("cornell_box"), util.default_camera(), 2048, 2048, rows=(1000, 1016),
                     threads=0)
@@ -134,7 +134,7 @@ def test_reference_example_binaries_run_unchanged(tmp_path):
     want = O.render(L.KERNEL_CUSTOM_BARY, util.scene("cornell_box"), util.default_camera(), 800, 800, threads=0)
     np.testing.assert_array_equal(pixels, (want * 255).astype(np.int8).view(np.uint8))
     # the command-line program on a scene file of this repo (2048x2048, basic.cu pipeline)
-    r = subprocess.run([cli, "resources/scenes/basic_cuda.scene"], cwd=util.ROOT, capture_output=True, text=True,
+    r = subprocess.run([cli, "resources/scenes/cornell_basic_cuda.scene"], cwd=util.ROOT, capture_output=True, text=True,
                        timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     out = os.path.join(util.ROOT, "output.jpg.ppm")
