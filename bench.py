@@ -203,6 +203,7 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true")
+    ap.add_argument("--no-cull", action="store_true", help="skip the secondary opt-in culled measurement")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -411,6 +412,32 @@ def main():
             line["cpu_baseline"] = {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "port",
                                     "sample": "frames 0..%d of the %d at full %dx%d (%.1f s of CPU work)" % (
                                         per - 1, frames, w, h, secs)}
+        if world == 1 and not args.no_cull:
+            # OPT-IN culled traversal (LT_FLAG_CULL): reported beside the headline, never instead of it.
+            # It does less work than the reference's traversal; identity of the full-size output is checked here.
+            ctx.set_stream(stream.cuda_stream)
+            exact = acc.clone()
+            pc = make_step_params(L.FLAG_CULL)
+            ctx.render_device(scene, cam, pc, acc.data_ptr(), sync=True)
+            identical = bool(torch.equal(acc.view(torch.int32), exact.view(torch.int32)))
+            times = []
+            for _ in range(max(2, min(args.steps, 3))):
+                flush.fill_(1.0)
+                c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                c0.record(stream)
+                ctx.render_device(scene, cam, pc, acc.data_ptr(), sync=False)
+                c1.record(stream)
+                torch.cuda.synchronize()
+                times.append(c0.elapsed_time(c1))
+            ctx.render_device(scene, cam, make_step_params(L.FLAG_CULL | L.FLAG_STATS), acc.data_ptr(), sync=True)
+            sc_ = ctx.stats()
+            cms = sum(times) / len(times)
+            line["culled_opt_in"] = {
+                "flag": "LT_FLAG_CULL (off by default)", "ms_per_step": cms, "value": rays / (cms * 1e-3) / 1e6,
+                "unit": "Mrays/s (same ray count as the exact run)", "output_bit_identical_to_exact": identical,
+                "node_tests_per_ray_actual": sc_.node_tests / max(1, sc_.rays),
+                "tri_tests_per_ray_actual": sc_.tri_tests / max(1, sc_.rays),
+                "speedup_vs_exact": ms_per_step / cms}
         if world == 1 and not args.no_ref_cuda:
             # the reference's CUDA kernel only exists for primary rays (basic.cu); same scene, same size
             ref = reference_cuda_kernel_rate(sb, w, h)

@@ -60,7 +60,9 @@ enum lt_accum_mode {
 enum lt_flags {
   LT_FLAG_STATS = 1 << 0, /* count rays / node tests / triangle tests in the reference's traversal order
                              (no any-hit early-out); results via lt_last_stats. Not for timed runs. */
-  LT_FLAG_CULL = 1 << 1,  /* reserved (opt-in culling by hit distance; not implemented: every mode is exact) */
+  LT_FLAG_CULL = 1 << 1,  /* OPT-IN, off by default: closest-hit rays skip subtrees entered beyond the current hit
+                             (+1e-4 relative margin).  Does less work than the reference's traversal; output is
+                             identical on every tested scene but that is validated, not guaranteed. */
   LT_FLAG_MEGAKERNEL = 1 << 2, /* stochastic kernels: force the one-thread-per-pixel persistent kernel */
   LT_FLAG_WAVEFRONT = 1 << 3   /* stochastic kernels: force the wavefront pipeline (default: chosen by size;
                                   both produce bit-identical output) */
@@ -134,6 +136,10 @@ int lt_accum_read(lt_ctx* ctx, float* host_out, uint64_t float_count);
  * ids = primitiveIndex, hit = hitType, tuv = t,u,v.  Any pointer may be NULL.  Host pointers. */
 int lt_primary_hits(lt_ctx* ctx, lt_scene* scene, const void* camera28, int kernel, int width, int height,
                     int32_t* ids, int32_t* hit, float* tuv);
+
+/* same with lt_flags (LT_FLAG_CULL), to validate the opt-in culled traversal against the exact one */
+int lt_primary_hits_flags(lt_ctx* ctx, lt_scene* scene, const void* camera28, int kernel, int flags, int width,
+                          int height, int32_t* ids, int32_t* hit, float* tuv);
 
 int lt_last_stats(const lt_ctx* ctx, lt_stats* out_stats);
 

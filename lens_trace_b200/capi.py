@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "liblt_b200.so")
 SYMBOLS = [
     "lt_api_version", "lt_ctx_create", "lt_ctx_destroy", "lt_last_error", "lt_ctx_set_stream", "lt_scene_upload",
     "lt_scene_release", "lt_render", "lt_render_device", "lt_accum_reset", "lt_accum_read", "lt_primary_hits",
-    "lt_last_stats", "lt_kernel_from_path", "lt_kernel_name", "lt_debug_random", "lt_debug_hemisphere", "lt_plugin_load", "lt_render_plugin",
+    "lt_last_stats", "lt_kernel_from_path", "lt_kernel_name", "lt_debug_random", "lt_debug_hemisphere", "lt_plugin_load", "lt_render_plugin", "lt_primary_hits_flags",
 ]
 
 
@@ -70,6 +70,8 @@ def load():
     lib.lt_accum_read.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
     lib.lt_primary_hits.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                     C.c_void_p, C.c_void_p]
+    lib.lt_primary_hits_flags.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                          C.c_void_p, C.c_void_p, C.c_void_p]
     lib.lt_last_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
     lib.lt_debug_random.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     lib.lt_debug_hemisphere.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
@@ -160,13 +162,14 @@ class Context:
     def accum_reset(self):
         self._check(self.lib.lt_accum_reset(self.h), "lt_accum_reset")
 
-    def primary_hits(self, scene, camera, kernel, width, height):
+    def primary_hits(self, scene, camera, kernel, width, height, flags=0):
         ids = np.empty((height, width), dtype=np.int32)
         hit = np.empty((height, width), dtype=np.int32)
         tuv = np.empty((height, width, 3), dtype=np.float32)
         cam = np.ascontiguousarray(camera, dtype=L.CAMERA)
-        self._check(self.lib.lt_primary_hits(self.h, scene.h, cam.ctypes.data, kernel, width, height, ids.ctypes.data,
-                                             hit.ctypes.data, tuv.ctypes.data), "lt_primary_hits")
+        self._check(self.lib.lt_primary_hits_flags(self.h, scene.h, cam.ctypes.data, kernel, flags, width, height,
+                                                   ids.ctypes.data, hit.ctypes.data, tuv.ctypes.data),
+                    "lt_primary_hits_flags")
         return ids, hit, tuv
 
     def plugin_load(self, path):

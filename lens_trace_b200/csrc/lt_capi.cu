@@ -343,11 +343,16 @@ static int render_common(lt_ctx* ctx, lt_scene* scene, const LtLaunch& L, float*
     static long long minPaths = -1, maxPaths = -1;
     if (minPaths < 0) {
       const char* e = getenv("LT_WAVEFRONT_MIN_PATHS");
-      minPaths = e ? atoll(e) : (1ll << 18);
+      minPaths = e ? atoll(e) : (1ll << 23);
       e = getenv("LT_WAVEFRONT_MAX_PATHS");
       maxPaths = e ? atoll(e) : (1ll << 24);
     }
-    wavefront = (L.flags & LT_FLAG_WAVEFRONT) || pixels * L.frames >= minPaths;
+    // measured (tools/compare_pipelines.py): the wavefront wins once ~8M paths are in flight per batch; below
+    // that, and for the two-ray lighting kernels on small scenes, its per-round launches and state traffic lose
+    bool isGI = (L.kernel == 5 || L.kernel == 6);
+    bool bigScene = scene->dev.nodeCount > 100000;
+    wavefront = (L.flags & (LT_FLAG_WAVEFRONT | LT_FLAG_CULL)) ||
+                (pixels * L.frames >= minPaths && (isGI || bigScene) && L.kernel != 5);
     if (wavefront) {
       long long cap = maxPaths;
       long long memCap = (long long)(ctx->totalMem / 8) / 200;  // at most 1/8 of the device for the workspace
@@ -362,7 +367,8 @@ static int render_common(lt_ctx* ctx, lt_scene* scene, const LtLaunch& L, float*
         ctx->wfBytes = 0;
         if (cudaMalloc(&ctx->wfWorkspace, need) != cudaSuccess) {
           cudaGetLastError();
-          if (L.flags & LT_FLAG_WAVEFRONT) return fail(ctx, LT_ERR_CUDA, "lt_render: cannot allocate the wavefront workspace");
+          if (L.flags & (LT_FLAG_WAVEFRONT | LT_FLAG_CULL))
+            return fail(ctx, LT_ERR_CUDA, "lt_render: cannot allocate the wavefront workspace");
           wavefront = false;  // not a fallback to other arithmetic: the megakernel is the same path per pixel
         } else {
           ctx->wfBytes = need;
@@ -488,8 +494,21 @@ extern "C" int lt_accum_read(lt_ctx* ctx, float* host_out, uint64_t float_count)
   return LT_OK;
 }
 
+static int primary_hits_impl(lt_ctx* ctx, lt_scene* scene, const void* camera28, int kernel, int flags, int width,
+                             int height, int32_t* ids, int32_t* hit, float* tuv);
+
 extern "C" int lt_primary_hits(lt_ctx* ctx, lt_scene* scene, const void* camera28, int kernel, int width, int height,
                                int32_t* ids, int32_t* hit, float* tuv) {
+  return primary_hits_impl(ctx, scene, camera28, kernel, 0, width, height, ids, hit, tuv);
+}
+
+extern "C" int lt_primary_hits_flags(lt_ctx* ctx, lt_scene* scene, const void* camera28, int kernel, int flags,
+                                     int width, int height, int32_t* ids, int32_t* hit, float* tuv) {
+  return primary_hits_impl(ctx, scene, camera28, kernel, flags, width, height, ids, hit, tuv);
+}
+
+static int primary_hits_impl(lt_ctx* ctx, lt_scene* scene, const void* camera28, int kernel, int flags, int width,
+                             int height, int32_t* ids, int32_t* hit, float* tuv) {
   if (!ctx) return fail(nullptr, LT_ERR_INVALID, "lt_primary_hits: ctx is NULL");
   if (!scene || !camera28 || width <= 0 || height <= 0 || kernel < 0 || kernel >= LT_KERNEL_COUNT)
     return fail(ctx, LT_ERR_INVALID, "lt_primary_hits: bad argument");
@@ -502,7 +521,7 @@ extern "C" int lt_primary_hits(lt_ctx* ctx, lt_scene* scene, const void* camera2
   CK(cudaMalloc(&dTuv, 3 * n * sizeof(float)));
   RefCamera cam;
   memcpy(&cam, camera28, sizeof(cam));
-  lt_launch_primary_hits(scene->dev, cam, kernel, width, height, dIds, dHit, dTuv, ctx->stream);
+  lt_launch_primary_hits(scene->dev, cam, kernel, flags, width, height, dIds, dHit, dTuv, ctx->stream);
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   if (e == cudaSuccess && ids) e = cudaMemcpy(ids, dIds, n * sizeof(int), cudaMemcpyDeviceToHost);

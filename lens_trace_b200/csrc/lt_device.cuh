@@ -300,6 +300,113 @@ __device__ __forceinline__ bool trav_iter(Trav& t, const LtSceneDev& sc, int* __
   return t.cur == LT_DONE && t.qHead == t.qTail;
 }
 
+// ------------------------------------------------------------------------------------------------
+// OPT-IN culled traversal (LT_FLAG_CULL): same tree, same order, same triangle arithmetic, but a
+// subtree is skipped when its box is entered farther along the ray than the current hit (plus a
+// margin of 1e-4 relative + 1e-5 absolute, ~100x the rounding error of t).  The reference never
+// culls (basic.cu:136-154 ignores the payload), so this does LESS work than the reference; the
+// output is identical unless a triangle's computed t undercuts its own box entry by more than the
+// margin, which no test scene exhibits (tests/test_gpu_parity.py::test_culling_is_output_identical),
+// but which is validated, not proven.  Closest-hit rays only; rays that need the select-chain slab
+// (non-finite reciprocals) are never culled.  Triangles are tested as soon as their leaf is reached.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool slab_fast_entry(float mnx, float mxx, float mny, float mxy, float mnz, float mxz,
+                                                const Ray& r, float ix, float iy, float iz, float& entry) {
+  float ax = FMUL(FSUB(mnx, r.ox), ix), bx = FMUL(FSUB(mxx, r.ox), ix);
+  float ay = FMUL(FSUB(mny, r.oy), iy), by = FMUL(FSUB(mxy, r.oy), iy);
+  float az = FMUL(FSUB(mnz, r.oz), iz), bz = FMUL(FSUB(mxz, r.oz), iz);
+  float lo = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
+  float hi = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+  entry = lo;
+  return lo <= hi && hi > 0.0f;
+}
+
+__device__ __forceinline__ float cull_limit(float t) { return t + (fabsf(t) * 1.0e-4f + 1.0e-5f); }
+
+// one step of the culled traversal: a box-pair test with culling, or a triangle test followed by
+// popping the next entry that survives the current limit.  tstk holds the entry distance of every
+// stacked reference ([level][thread], like stk).
+template <bool STATS>
+__device__ __forceinline__ void trav_step_cull(Trav& t, const LtSceneDev& sc, int* __restrict__ stk,
+                                               float* __restrict__ tstk, float epsThr, LtCounters& cnt) {
+  if (t.cur >= 0) {
+    const float4* np = reinterpret_cast<const float4*>(sc.wnodes + t.cur);
+    float4 bx = __ldg(np), by = __ldg(np + 1), bz = __ldg(np + 2);
+    int4 m = __ldg(reinterpret_cast<const int4*>(np) + 3);
+    bool hl, hr;
+    float el = -FLT_MAX, er = -FLT_MAX;
+    if (t.negMask & LT_EXACT_SLAB) {
+      bool nx = t.negMask & 1u, ny = t.negMask & 2u, nz = t.negMask & 4u;
+      hl = slab(nx ? bx.y : bx.x, nx ? bx.x : bx.y, ny ? by.y : by.x, ny ? by.x : by.y, nz ? bz.y : bz.x,
+                nz ? bz.x : bz.y, t.r, t.ix, t.iy, t.iz);
+      hr = slab(nx ? bx.w : bx.z, nx ? bx.z : bx.w, ny ? by.w : by.z, ny ? by.z : by.w, nz ? bz.w : bz.z,
+                nz ? bz.z : bz.w, t.r, t.ix, t.iy, t.iz);
+    } else {
+      hl = slab_fast_entry(bx.x, bx.y, by.x, by.y, bz.x, bz.y, t.r, t.ix, t.iy, t.iz, el);
+      hr = slab_fast_entry(bx.z, bx.w, by.z, by.w, bz.z, bz.w, t.r, t.ix, t.iy, t.iz, er);
+    }
+    if (STATS) cnt.nodeTests += 2;
+    float lim = cull_limit(t.h.t);
+    hl = hl && !(el > lim);
+    hr = hr && !(er > lim);
+    bool axisNeg = (t.negMask >> m.z) & 1u;
+    int nearRef = axisNeg ? m.y : m.x, farRef = axisNeg ? m.x : m.y;
+    float farEntry = axisNeg ? el : er;
+    bool hn = axisNeg ? hr : hl, hf = axisNeg ? hl : hr;
+    if (hn) {
+      t.cur = nearRef;
+      if (hf) {
+        stk[t.sp * LT_BLOCK] = farRef;
+        tstk[t.sp * LT_BLOCK] = farEntry;
+        t.sp++;
+      }
+      return;
+    }
+    if (hf) {
+      t.cur = farRef;
+      return;
+    }
+  } else {
+    int prim = ~t.cur;
+    if (prim != t.ignore) {
+      if (STATS) cnt.triTests++;
+      if (tri_test(sc.tris, prim, t.r, epsThr, t.h)) {
+        t.h.prim = prim;
+        t.h.hit = 1;
+      }
+    }
+  }
+  // pop the next stacked reference whose box entry is still within the limit
+  float lim = cull_limit(t.h.t);
+  t.cur = LT_DONE;
+  while (t.sp > 0) {
+    t.sp--;
+    if (!(tstk[t.sp * LT_BLOCK] > lim)) {
+      t.cur = stk[t.sp * LT_BLOCK];
+      break;
+    }
+  }
+}
+
+template <bool STATS>
+__device__ __forceinline__ void trace_cull(Trav& t, const LtSceneDev& sc, int ignore, float tInit, float epsThr,
+                                           int* __restrict__ stk, float* __restrict__ tstk, LtCounters& cnt) {
+  trav_begin<STATS>(t, sc, ignore, tInit, false, cnt);
+  while (t.cur != LT_DONE) trav_step_cull<STATS>(t, sc, stk, tstk, epsThr, cnt);
+}
+
+// dynamic shared memory of every traversal kernel: [stackDepth][LT_BLOCK] stack, [LT_MAX_BATCH][LT_BLOCK] leaf
+// list/FIFO, [stackDepth][LT_BLOCK] entry distances (culled mode only)
+__host__ __device__ inline int lt_stack_levels(const LtSceneDev& sc) { return sc.stackDepth < 1 ? 1 : sc.stackDepth; }
+__host__ inline size_t lt_traversal_smem(const LtSceneDev& sc, bool cull) {
+  return (size_t)(lt_stack_levels(sc) * (cull ? 2 : 1) + LT_MAX_BATCH) * LT_BLOCK * sizeof(int);
+}
+#define LT_SMEM_POINTERS(sc)                                                            \
+  extern __shared__ int smemStack[];                                                    \
+  int* stk = smemStack + threadIdx.x;                                                   \
+  int* list = smemStack + lt_stack_levels(sc) * LT_BLOCK + threadIdx.x;                 \
+  float* tstk = reinterpret_cast<float*>(smemStack + (lt_stack_levels(sc) + LT_MAX_BATCH) * LT_BLOCK) + threadIdx.x;
+
 // run one ray to completion (deterministic kernels, hit-record kernel)
 template <bool STATS>
 __device__ __forceinline__ void trace(Trav& t, const LtSceneDev& sc, int ignore, float tInit, float epsThr,
@@ -412,7 +519,7 @@ __device__ __forceinline__ void lerp_fused(const float* a, const float* b, const
 // On entry t holds the primary ray and its hit; on exit the refracted ray and its hit.
 template <bool STATS>
 __device__ void lens_path(const LtSceneDev& sc, Trav& t, float tInit, float epsThr, int* stk, int* list,
-                          LtCounters& cnt) {
+                          float* tstk, bool cull, LtCounters& cnt) {
   const RefPrim* prim = sc.prims + t.h.prim;
   const RefMaterial* mat = sc.mats + prim->materialIndex;
   int firstPrim = t.h.prim;
@@ -432,7 +539,8 @@ __device__ void lens_path(const LtSceneDev& sc, Trav& t, float tInit, float epsT
   float r2w = FFMA(n, 0.0f, FMUL(k, 0.0f));
   t.r.ox = pos[0]; t.r.oy = pos[1]; t.r.oz = pos[2];
   t.r.dx = dx; t.r.dy = dy; t.r.dz = dz;
-  trace<STATS>(t, sc, firstPrim, tInit, epsThr, false, stk, list, cnt);
+  if (cull) trace_cull<STATS>(t, sc, firstPrim, tInit, epsThr, stk, tstk, cnt);
+  else trace<STATS>(t, sc, firstPrim, tInit, epsThr, false, stk, list, cnt);
 
   int secondPrim = t.h.prim;
   prim = sc.prims + secondPrim;
@@ -451,7 +559,8 @@ __device__ void lens_path(const LtSceneDev& sc, Trav& t, float tInit, float epsT
   dz = FFMA(t.r.dz, ior, -FMUL(k2, nrm[2]));
   t.r.ox = pos[0]; t.r.oy = pos[1]; t.r.oz = pos[2];
   t.r.dx = dx; t.r.dy = dy; t.r.dz = dz;
-  trace<STATS>(t, sc, secondPrim, tInit, epsThr, false, stk, list, cnt);
+  if (cull) trace_cull<STATS>(t, sc, secondPrim, tInit, epsThr, stk, tstk, cnt);
+  else trace<STATS>(t, sc, secondPrim, tInit, epsThr, false, stk, list, cnt);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -109,7 +109,7 @@ size_t lt_scan_temp_bytes(int n);
 int lt_launch_exclusive_scan(void* dTemp, size_t tempBytes, const int* dIn, int* dOut, int n, cudaStream_t stream);
 int lt_launch_render(const LtSceneDev& sc, const LtLaunch& L, float* dOut, LtCounters* dCounters,
                      cudaStream_t stream);
-int lt_launch_primary_hits(const LtSceneDev& sc, const RefCamera& cam, int kernel, int width, int height,
+int lt_launch_primary_hits(const LtSceneDev& sc, const RefCamera& cam, int kernel, int flags, int width, int height,
                            int* dIds, int* dHit, float* dTuv, cudaStream_t stream);
 int lt_launch_debug_random(const float* fx, const float* fy, const float* seed, int n, float* out, cudaStream_t stream);
 int lt_launch_debug_hemisphere(const float* u1, const float* u2, const float* up, int n, float* out,

@@ -21,9 +21,7 @@
 template <bool STATS>
 __global__ void __launch_bounds__(LT_BLOCK) k_flat(LtSceneDev sc, LtLaunch L, float* __restrict__ out,
                                                    LtCounters* gcnt) {
-  extern __shared__ int smemStack[];
-  int* stk = smemStack + threadIdx.x;
-  int* list = smemStack + max(sc.stackDepth, 1) * LT_BLOCK + threadIdx.x;
+  LT_SMEM_POINTERS(sc)
   int px, py;
   if (!thread_pixel(L.width, L.height, px, py)) return;
   LtCounters cnt = {0, 0, 0};
@@ -32,7 +30,9 @@ __global__ void __launch_bounds__(LT_BLOCK) k_flat(LtSceneDev sc, LtLaunch L, fl
   t.r = camera_ray(L.cam, px, py, L.width, L.height, fx, fy);
   const float tInit = lt_tinit(L.kernel), epsThr = lt_eps(L.kernel);
   float color[3] = {0.0f, 0.0f, 0.0f};
-  trace<STATS>(t, sc, -1, tInit, epsThr, false, stk, list, cnt);
+  const bool cull = (L.flags & 2) != 0;  // LT_FLAG_CULL
+  if (cull) trace_cull<STATS>(t, sc, -1, tInit, epsThr, stk, tstk, cnt);
+  else trace<STATS>(t, sc, -1, tInit, epsThr, false, stk, list, cnt);
   if (t.h.hit == 1) {
     if (L.kernel == 2) {  // custom_opencl.cl:240
       color[0] = t.h.u;
@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(LT_BLOCK) k_flat(LtSceneDev sc, LtLaunch L, fl
     } else {  // basic.cu:312-326
       const RefMaterial* mat = sc.mats + sc.prims[t.h.prim].materialIndex;
       if (mat->dissolve < 1.0f) {
-        lens_path<STATS>(sc, t, tInit, epsThr, stk, list, cnt);
+        lens_path<STATS>(sc, t, tInit, epsThr, stk, list, tstk, cull, cnt);
         if (t.h.hit == 1) mat = sc.mats + sc.prims[t.h.prim].materialIndex;
       }
       color[0] = mat->diffuse[0];
@@ -74,9 +74,8 @@ __global__ void __launch_bounds__(LT_BLOCK) k_flat(LtSceneDev sc, LtLaunch L, fl
 template <bool STATS>
 __global__ void __launch_bounds__(LT_BLOCK) k_path(LtSceneDev sc, LtLaunch L, float* __restrict__ out,
                                                    LtCounters* gcnt) {
-  extern __shared__ int smemStack[];
-  int* stk = smemStack + threadIdx.x;
-  int* list = smemStack + max(sc.stackDepth, 1) * LT_BLOCK + threadIdx.x;
+  LT_SMEM_POINTERS(sc)
+  (void)tstk;  // the persistent megakernel does not cull (LT_FLAG_CULL selects the wavefront pipeline)
   int px, py;
   bool alive = thread_pixel(L.width, L.height, px, py);
   LtCounters cnt = {0, 0, 0};
@@ -167,19 +166,18 @@ __global__ void __launch_bounds__(LT_BLOCK) k_path(LtSceneDev sc, LtLaunch L, fl
 // ------------------------------------------------------------------------------------------------
 // primary hit records (parity/debug output)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(LT_BLOCK) k_primary_hits(LtSceneDev sc, RefCamera cam, int kernel, int width,
-                                                           int height, int* __restrict__ ids, int* __restrict__ hit,
-                                                           float* __restrict__ tuv) {
-  extern __shared__ int smemStack[];
-  int* stk = smemStack + threadIdx.x;
-  int* list = smemStack + max(sc.stackDepth, 1) * LT_BLOCK + threadIdx.x;
+__global__ void __launch_bounds__(LT_BLOCK) k_primary_hits(LtSceneDev sc, RefCamera cam, int kernel, int flags,
+                                                           int width, int height, int* __restrict__ ids,
+                                                           int* __restrict__ hit, float* __restrict__ tuv) {
+  LT_SMEM_POINTERS(sc)
   int px, py;
   if (!thread_pixel(width, height, px, py)) return;
   LtCounters cnt = {0, 0, 0};
   float fx, fy;
   Trav t;
   t.r = camera_ray(cam, px, py, width, height, fx, fy);
-  trace<false>(t, sc, -1, lt_tinit(kernel), lt_eps(kernel), false, stk, list, cnt);
+  if (flags & 2) trace_cull<false>(t, sc, -1, lt_tinit(kernel), lt_eps(kernel), stk, tstk, cnt);
+  else trace<false>(t, sc, -1, lt_tinit(kernel), lt_eps(kernel), false, stk, list, cnt);
   const Hit h = t.h;
   long long i = (long long)py * width + px;
   if (ids) ids[i] = h.prim;
@@ -283,17 +281,14 @@ int lt_launch_reflatten(const RefNode* dNodes, int nodeCount, const RefPrim* dPr
   return 2;
 }
 
-static size_t stack_bytes(const LtSceneDev& sc) {
-  int d = sc.stackDepth < 1 ? 1 : sc.stackDepth;
-  return (size_t)(d + LT_MAX_BATCH) * LT_BLOCK * sizeof(int);
-}
+static size_t stack_bytes(const LtSceneDev& sc, bool cull) { return lt_traversal_smem(sc, cull); }
 
 static int tile_blocks(int width, int height) { return ((width + 15) / 16) * ((height + 7) / 8); }
 
 int lt_launch_render(const LtSceneDev& sc, const LtLaunch& L, float* dOut, LtCounters* dCounters,
                      cudaStream_t stream) {
   int blocks = tile_blocks(L.width, L.height);
-  size_t smem = stack_bytes(sc);
+  size_t smem = stack_bytes(sc, (L.flags & 2) != 0);
   bool stats = (L.flags & 1) != 0;
   bool flat = (L.kernel <= 2);
   if (flat) {
@@ -306,9 +301,9 @@ int lt_launch_render(const LtSceneDev& sc, const LtLaunch& L, float* dOut, LtCou
   return 1;
 }
 
-int lt_launch_primary_hits(const LtSceneDev& sc, const RefCamera& cam, int kernel, int width, int height,
+int lt_launch_primary_hits(const LtSceneDev& sc, const RefCamera& cam, int kernel, int flags, int width, int height,
                            int* dIds, int* dHit, float* dTuv, cudaStream_t stream) {
-  k_primary_hits<<<tile_blocks(width, height), LT_BLOCK, stack_bytes(sc), stream>>>(sc, cam, kernel, width, height,
-                                                                                    dIds, dHit, dTuv);
+  k_primary_hits<<<tile_blocks(width, height), LT_BLOCK, stack_bytes(sc, (flags & 2) != 0), stream>>>(
+      sc, cam, kernel, flags, width, height, dIds, dHit, dTuv);
   return 1;
 }

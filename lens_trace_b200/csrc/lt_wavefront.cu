@@ -71,9 +71,8 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_generate(LtLaunch L, LtWfBuffer
 template <bool STATS>
 __global__ void __launch_bounds__(WF_BLOCK) k_wf_primary(LtSceneDev sc, LtLaunch L, LtWfBuffers B, long long nPaths,
                                                          int pixels, int sample, LtCounters* gcnt) {
-  extern __shared__ int smemStack[];
-  int* stk = smemStack + threadIdx.x;
-  int* list = smemStack + max(sc.stackDepth, 1) * LT_BLOCK + threadIdx.x;
+  LT_SMEM_POINTERS(sc)
+  const bool cull = (L.flags & 2) != 0;  // LT_FLAG_CULL: closest-hit rays skip subtrees behind the current hit
   const PathConsts pc = path_consts(L);
   const unsigned lane = threadIdx.x & 31u;
   LtCounters cnt = {0, 0, 0};
@@ -91,7 +90,8 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_primary(LtSceneDev sc, LtLaunch
       pixel_of_path(p, pixels, L.width, px, py, fl);
       float fx, fy;
       t.r = camera_ray(L.cam, px, py, L.width, L.height, fx, fy);
-      trace<STATS>(t, sc, -1, pc.tInit, pc.epsThr, false, stk, list, cnt);
+      if (cull) trace_cull<STATS>(t, sc, -1, pc.tInit, pc.epsThr, stk, tstk, cnt);
+      else trace<STATS>(t, sc, -1, pc.tInit, pc.epsThr, false, stk, list, cnt);
       PathState ps;
       ps.nrm[0] = ps.nrm[1] = ps.nrm[2] = 0.0f;
       ps.diffuse[0] = ps.diffuse[1] = ps.diffuse[2] = 0.0f;
@@ -148,9 +148,8 @@ __global__ void k_wf_reset(LtWfBuffers B) {
 template <bool STATS>
 __global__ void __launch_bounds__(WF_BLOCK) k_wf_trace(LtSceneDev sc, LtLaunch L, LtWfBuffers B, int q,
                                                        LtCounters* gcnt) {
-  extern __shared__ int smemStack[];
-  int* stk = smemStack + threadIdx.x;
-  int* list = smemStack + max(sc.stackDepth, 1) * LT_BLOCK + threadIdx.x;
+  LT_SMEM_POINTERS(sc)
+  const bool cull = (L.flags & 2) != 0;  // LT_FLAG_CULL: closest-hit rays skip subtrees behind the current hit
   const int n = B.counts[q];
   const float epsThr = lt_eps(L.kernel);
   const unsigned lane = threadIdx.x & 31u;
@@ -199,7 +198,15 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_trace(LtSceneDev sc, LtLaunch L
       continue;  // every ray just fetched missed the root box: fetch again
     }
     if (has) {
-      if (trav_iter<STATS>(t, sc, stk, list, epsThr, L.iterNodeSteps, L.iterTriTests, cnt)) {
+      bool finished;
+      if (cull && !t.anyHit) {  // a round holds one kind of ray, so this does not split warps
+        for (int k = 0; k < 2 * L.iterNodeSteps && t.cur != LT_DONE; k++)
+          trav_step_cull<STATS>(t, sc, stk, tstk, epsThr, cnt);
+        finished = t.cur == LT_DONE;
+      } else {
+        finished = trav_iter<STATS>(t, sc, stk, list, epsThr, L.iterNodeSteps, L.iterTriTests, cnt);
+      }
+      if (finished) {
         B.hits[entry] = make_float4(t.h.t, t.h.u, t.h.v,
                                     __int_as_float((int)((unsigned)t.h.prim | (t.h.hit ? 0x80000000u : 0u))));
         entry = -1;
@@ -362,8 +369,11 @@ int lt_launch_render_wavefront(const LtSceneDev& sc, const LtLaunch& L, float* d
   const int samples = (L.kernel == 3 || L.kernel == 5) ? 25 : 1;
   const int maxDepth = L.maxRayDepth > 0 ? L.maxRayDepth : 16;
   const int rounds = isGI ? 2 + 2 * maxDepth : 2;
-  const size_t smem = (size_t)((sc.stackDepth < 1 ? 1 : sc.stackDepth) + LT_MAX_BATCH) * LT_BLOCK * sizeof(int);
-  const int persistentBlocks = smCount * 8;
+  const size_t smem = lt_traversal_smem(sc, (L.flags & 2) != 0);
+  int blocksPerSm = (int)((200 * 1024) / smem);  // shared memory is what limits residency of the persistent kernel
+  if (blocksPerSm > 8) blocksPerSm = 8;
+  if (blocksPerSm < 1) blocksPerSm = 1;
+  const int persistentBlocks = smCount * blocksPerSm;
   int launches = 0;
   for (int frame0 = 0; frame0 < L.frames; frame0 += batchFrames) {
     int nf = L.frames - frame0 < batchFrames ? L.frames - frame0 : batchFrames;

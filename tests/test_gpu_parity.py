@@ -234,6 +234,50 @@ def test_full_size_properties(ctx):
     assert_images_match(two[600:620], acc[600:620], "GI rows 600-620 at 1080p", max_outliers=3)
 
 
+@pytest.mark.parametrize("name", ["green_wall", "cornell_box", "cornell_box_lens", "single", "multi_leaf"])
+def test_culling_is_output_identical(ctx, name):
+    """LT_FLAG_CULL (opt-in) does less work than the reference traversal; on every test scene its output --
+    hit ids, t/u/v, colours, GI samples -- is bit-identical to the exact mode."""
+    sb, sc = gpu_scene(ctx, name)
+    for yaw in (0.0, 0.04, -0.07):
+        cam = util.default_camera(yaw, 2)
+        a = ctx.primary_hits(sc, cam, L.KERNEL_BASIC_CU, 320, 200)
+        b = ctx.primary_hits(sc, cam, L.KERNEL_BASIC_CU, 320, 200, flags=L.FLAG_CULL)
+        np.testing.assert_array_equal(a[0], b[0])
+        np.testing.assert_array_equal(a[1], b[1])
+        util.assert_bit_equal(a[2], b[2], "t,u,v culled vs exact")
+        for kernel in (L.KERNEL_BASIC_CU, L.KERNEL_CUSTOM_BARY, L.KERNEL_ACCUMULATOR, L.KERNEL_GI):
+            exact = ctx.render(sc, cam, capi.make_params(kernel, 200, 120, max_ray_depth=4))
+            culled = ctx.render(sc, cam, capi.make_params(kernel, 200, 120, max_ray_depth=4, flags=L.FLAG_CULL))
+            util.assert_bit_equal(culled, exact, "%s kernel %d culled vs exact" % (name, kernel))
+
+
+def test_culling_on_a_synthetic_mesh(ctx, tmp_path):
+    from lens_trace_b200 import host
+    p = str(tmp_path / "synth.obj")
+    host.write_synthetic_scene(p, 160, 0x5EED)  # 51 212 triangles
+    sb = host.load_scene_buffers(p)
+    sc = ctx.upload(sb)
+    cam = util.default_camera(0.0, 1)
+    a = ctx.primary_hits(sc, cam, L.KERNEL_GI, 640, 360)
+    b = ctx.primary_hits(sc, cam, L.KERNEL_GI, 640, 360, flags=L.FLAG_CULL)
+    np.testing.assert_array_equal(a[0], b[0])
+    util.assert_bit_equal(a[2], b[2])
+    p_exact = capi.make_params(L.KERNEL_GI, 320, 180, max_ray_depth=4, frames=2, accum_mode=L.ACCUM_RUNNING_MEAN,
+                               flags=L.FLAG_STATS)
+    p_cull = capi.make_params(L.KERNEL_GI, 320, 180, max_ray_depth=4, frames=2, accum_mode=L.ACCUM_RUNNING_MEAN,
+                              flags=L.FLAG_STATS | L.FLAG_CULL)
+    ctx.accum_reset()
+    exact = ctx.render(sc, cam, p_exact)
+    n_exact = ctx.stats().node_tests
+    ctx.accum_reset()
+    culled = ctx.render(sc, cam, p_cull)
+    n_cull = ctx.stats().node_tests
+    util.assert_bit_equal(culled, exact, "synthetic GI culled vs exact")
+    assert n_cull < n_exact  # it really does less work
+    sc.release()
+
+
 def test_bad_arguments_are_errors(ctx):
     sb, sc = gpu_scene(ctx, "cornell_box")
     with pytest.raises(capi.LtError):
