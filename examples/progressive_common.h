@@ -59,6 +59,11 @@ inline int runProgressiveExample(const char* kernelPath, int argc, char** argv) 
   auto t0 = std::chrono::steady_clock::now();
   camera.resetFrameCount();  // a camera move restarts the accumulation with frameCount = 0
   if (perFrame) {
+    RenderExtensionB200 one = {};  // only to forward --depth; one frame, no device accumulation
+    one.sType = STRUCTURE_TYPE_RENDER_EXTENSION_B200;
+    one.frames = 1;
+    one.maxRayDepth = maxDepth;
+    props.pNext = &one;
     for (uint32_t f = 0; f < frames; f++) {
       renderer.render(&props);
       uint32_t fc = camera.getFrameCount();

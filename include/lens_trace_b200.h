@@ -137,7 +137,7 @@ int lt_accum_read(lt_ctx* ctx, float* host_out, uint64_t float_count);
 int lt_primary_hits(lt_ctx* ctx, lt_scene* scene, const void* camera28, int kernel, int width, int height,
                     int32_t* ids, int32_t* hit, float* tuv);
 
-/* same with lt_flags (LT_FLAG_CULL), to validate the opt-in culled traversal against the exact one */
+/* same, taking flags of enum lt_flags [LT_FLAG_CULL], to validate the opt-in culled traversal against the exact one */
 int lt_primary_hits_flags(lt_ctx* ctx, lt_scene* scene, const void* camera28, int kernel, int flags, int width,
                           int height, int32_t* ids, int32_t* hit, float* tuv);
 

@@ -226,12 +226,13 @@ void initMaterial(material_t* m) {
 
 bool readLine(FILE* f, std::string* line) {
   line->clear();
-  int ch;
+  char buf[4096];
   bool any = false;
-  while ((ch = fgetc(f)) != EOF) {
+  while (fgets(buf, sizeof buf, f)) {
     any = true;
-    if (ch == '\n') break;
-    line->push_back((char)ch);
+    size_t n = strlen(buf);
+    line->append(buf, n);
+    if (n > 0 && buf[n - 1] == '\n') break;
   }
   while (!line->empty() && (line->back() == '\r' || line->back() == '\n')) line->pop_back();
   return any;
@@ -307,6 +308,8 @@ bool LoadObj(attrib_t* attrib, std::vector<shape_t>* shapes, std::vector<materia
     if (err) *err += std::string("Cannot open file [") + filename + "]\n";
     return false;
   }
+  std::vector<char> ioBuffer(1 << 20);
+  setvbuf(f, ioBuffer.data(), _IOFBF, ioBuffer.size());
   std::string baseDir;
   {
     std::string fn(filename);

@@ -213,3 +213,38 @@ def test_reference_kernel_source_as_a_plugin():
             util.assert_bit_equal(a, b, "%s yaw %g: reference source as plug-in vs built-in pipeline" % (name, yaw))
         sc.release()
     ctx.close()
+
+
+def test_headless_examples_build_and_run(tmp_path):
+    """examples/: the three example programs and the CLI, built against liblenstrace.so, run from the repo root."""
+    import subprocess
+    subprocess.check_call(["make", "-C", os.path.join(util.ROOT, "examples"), "-s"])
+    out = str(tmp_path / "gi.pfm")
+    r = subprocess.run([os.path.join(util.ROOT, "examples", "bin", "global_illumination"), "--size", "160", "120",
+                        "--frames", "6", "--depth", "4", "--out", out], cwd=util.ROOT, capture_output=True, text=True,
+                       timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    raw = open(out, "rb").read()
+    header = b"PF\n160 120\n-1.0\n"
+    assert raw.startswith(header)
+    batched = np.frombuffer(raw[len(header):], dtype=np.float32).reshape(120, 160, 3)
+    # the per-frame protocol of the reference's example (one render() per frame, mean on the host) gives the same picture
+    out2 = str(tmp_path / "gi2.pfm")
+    r = subprocess.run([os.path.join(util.ROOT, "examples", "bin", "global_illumination"), "--size", "160", "120",
+                        "--frames", "6", "--depth", "4", "--per-frame", "--out", out2], cwd=util.ROOT,
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    raw2 = open(out2, "rb").read()
+    per_frame = np.frombuffer(raw2[len(header):], dtype=np.float32).reshape(120, 160, 3)
+    acc = np.zeros((120, 160, 3), np.float32)
+    sb = util.scene("cornell_box")
+    for f in range(6):
+        O.accumulate(acc, O.render(L.KERNEL_GI, sb, util.default_camera(0.0, f), 160, 120, max_ray_depth=4, threads=0), f)
+    assert ((util.bits(batched) != util.bits(acc)).any(axis=-1)).sum() <= 3
+    np.testing.assert_allclose(batched, acc, rtol=1e-4, atol=1e-6)
+    util.assert_bit_equal(per_frame, batched, "one render() per frame + host mean vs one batched render()")
+    for exe, args in (("accumulator", ["--size", "96", "64", "--frames", "3", "--out", str(tmp_path / "a.ppm")]),
+                      ("custom_kernel", ["96", "64", str(tmp_path / "c.ppm")])):
+        r = subprocess.run([os.path.join(util.ROOT, "examples", "bin", exe)] + args, cwd=util.ROOT, capture_output=True,
+                           text=True, timeout=300)
+        assert r.returncode == 0, r.stdout + r.stderr
