@@ -300,7 +300,7 @@ static int check_params(lt_ctx* ctx, const lt_scene* scene, const void* camera28
       e = getenv("LT_BATCH_CLOSEST");
       bClosest = e ? atoi(e) : 16;
       bAny = bAny < 1 ? 1 : (bAny > 16 ? 16 : bAny);
-      bClosest = bClosest < 1 ? 1 : (bClosest > 16 ? 16 : bClosest);
+      bClosest = bClosest < 0 ? 0 : (bClosest > 16 ? 16 : bClosest);  // 0 selects the pipelined form in k_path
     }
     L->batchAnyHit = bAny;
     L->batchClosest = bClosest;
@@ -309,7 +309,7 @@ static int check_params(lt_ctx* ctx, const lt_scene* scene, const void* camera28
       const char* e = getenv("LT_ITER_NODE_STEPS");
       iterNodes = e ? atoi(e) : 8;
       e = getenv("LT_ITER_TRI_TESTS");
-      iterTris = e ? atoi(e) : 2;
+      iterTris = e ? atoi(e) : 3;
       if (iterNodes < 1) iterNodes = 1;
       if (iterTris < 1) iterTris = 1;
     }

@@ -300,6 +300,104 @@ __device__ __forceinline__ bool trav_iter(Trav& t, const LtSceneDev& sc, int* __
   return t.cur == LT_DONE && t.qHead == t.qTail;
 }
 
+// ---- lean form of trav_iter for the persistent queue-fed kernel ---------------------------------
+// Same semantics; written for instruction count: shared memory is addressed through 32-bit shared
+// addresses (no generic-pointer conversion per access), the two children of a node are classified once
+// and a hit leaf child is recorded in the FIFO inside the node step itself (no pop/drain round trip);
+// only a leaf that had to wait on the stack behind an inner sibling is recorded after being popped.
+__device__ __forceinline__ void sts32(unsigned addr, int v) {
+  asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ int lds32(unsigned addr) {
+  int v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+#define LT_SMEM_STRIDE_LOG2 9  // LT_BLOCK * sizeof(int) = 512 bytes between levels of one thread
+
+template <bool STATS>
+__device__ __forceinline__ bool trav_iter_lean(Trav& t, const LtSceneDev& sc, unsigned stkAddr, unsigned fifoAddr,
+                                               float epsThr, int nodeSteps, int triTests, LtCounters& cnt) {
+  for (int steps = 0; steps < nodeSteps && t.cur != LT_DONE && t.qTail - t.qHead <= LT_MAX_BATCH - 2; steps++) {
+    if (t.cur >= 0) {
+      const float4* np = reinterpret_cast<const float4*>(sc.wnodes + t.cur);
+      float4 bx = __ldg(np), by = __ldg(np + 1), bz = __ldg(np + 2);
+      int4 m = __ldg(reinterpret_cast<const int4*>(np) + 3);
+      unsigned hits;  // bit 0: left child box hit, bit 1: right child box hit
+      if (__any_sync(__activemask(), (t.negMask & LT_EXACT_SLAB) != 0u)) {
+        bool nx = t.negMask & 1u, ny = t.negMask & 2u, nz = t.negMask & 4u;
+        bool hl = slab(nx ? bx.y : bx.x, nx ? bx.x : bx.y, ny ? by.y : by.x, ny ? by.x : by.y, nz ? bz.y : bz.x,
+                       nz ? bz.x : bz.y, t.r, t.ix, t.iy, t.iz);
+        bool hr = slab(nx ? bx.w : bx.z, nx ? bx.z : bx.w, ny ? by.w : by.z, ny ? by.z : by.w, nz ? bz.w : bz.z,
+                       nz ? bz.z : bz.w, t.r, t.ix, t.iy, t.iz);
+        hits = (hl ? 1u : 0u) | (hr ? 2u : 0u);
+      } else {
+        bool hl = slab_fast(bx.x, bx.y, by.x, by.y, bz.x, bz.y, t.r, t.ix, t.iy, t.iz);
+        bool hr = slab_fast(bx.z, bx.w, by.z, by.w, bz.z, bz.w, t.r, t.ix, t.iy, t.iz);
+        hits = (hl ? 1u : 0u) | (hr ? 2u : 0u);
+      }
+      if (STATS) {
+        cnt.nodeTests += 2;
+        unsigned lc = (unsigned)m.w & 0xffffu, rc = (unsigned)m.w >> 16;
+        if ((hits & 1u) && m.x < 0 && lc > 1 && ~m.x != t.ignore) cnt.triTests += lc - 1;
+        if ((hits & 2u) && m.y < 0 && rc > 1 && ~m.y != t.ignore) cnt.triTests += rc - 1;
+      }
+      // near child first by the sign of the direction on the split axis (basic.cu:180-186)
+      bool axisNeg = (t.negMask >> m.z) & 1u;
+      int nearRef = axisNeg ? m.y : m.x, farRef = axisNeg ? m.x : m.y;
+      bool hn = (hits & (axisNeg ? 2u : 1u)) != 0u, hf = (hits & (axisNeg ? 1u : 2u)) != 0u;
+      bool nearInner = hn && nearRef >= 0;       // descend into near; far (if hit) must wait on the stack
+      bool recNear = hn && nearRef < 0 && ~nearRef != t.ignore;
+      bool farNow = hf && !nearInner;            // far is next in order right away
+      bool recFar = farNow && farRef < 0 && ~farRef != t.ignore;
+      if (recNear) {
+        sts32(fifoAddr + ((unsigned)(t.qTail & (LT_MAX_BATCH - 1)) << LT_SMEM_STRIDE_LOG2), ~nearRef);
+        t.qTail++;
+      }
+      if (recFar) {
+        sts32(fifoAddr + ((unsigned)(t.qTail & (LT_MAX_BATCH - 1)) << LT_SMEM_STRIDE_LOG2), ~farRef);
+        t.qTail++;
+      }
+      bool push = hf && nearInner;
+      bool farInner = farNow && farRef >= 0;
+      bool pop = !nearInner && !farInner;
+      bool canPop = pop && t.sp > 0;
+      t.sp -= canPop ? 1 : 0;
+      unsigned slot = stkAddr + ((unsigned)t.sp << LT_SMEM_STRIDE_LOG2);
+      int popped = lds32(slot);
+      if (push) sts32(slot, farRef);
+      t.sp += push ? 1 : 0;
+      t.cur = nearInner ? nearRef : (farInner ? farRef : (canPop ? popped : LT_DONE));
+    }
+    // a leaf that waited on the stack (or the root itself): record it and take the next entry
+    if (t.cur < 0 && t.cur != LT_DONE) {
+      int prim = ~t.cur;
+      if (prim != t.ignore) {
+        sts32(fifoAddr + ((unsigned)(t.qTail & (LT_MAX_BATCH - 1)) << LT_SMEM_STRIDE_LOG2), prim);
+        t.qTail++;
+      }
+      bool can = t.sp > 0;
+      t.sp -= can ? 1 : 0;
+      int v = lds32(stkAddr + ((unsigned)t.sp << LT_SMEM_STRIDE_LOG2));
+      t.cur = can ? v : LT_DONE;
+    }
+  }
+  for (int k = 0; k < triTests && t.qHead != t.qTail; k++) {
+    int prim = lds32(fifoAddr + ((unsigned)(t.qHead & (LT_MAX_BATCH - 1)) << LT_SMEM_STRIDE_LOG2));
+    t.qHead++;
+    if (STATS) cnt.triTests++;
+    if (tri_test(sc.tris, prim, t.r, epsThr, t.h)) {
+      t.h.prim = prim;
+      t.h.hit = 1;
+      if (t.anyHit) {
+        t.cur = LT_DONE;
+        t.qHead = t.qTail;
+      }
+    }
+  }
+  return t.cur == LT_DONE && t.qHead == t.qTail;
+}
+
 // ------------------------------------------------------------------------------------------------
 // OPT-IN culled traversal (LT_FLAG_CULL): same tree, same order, same triangle arithmetic, but a
 // subtree is skipped when its box is entered farther along the ray than the current hit (plus a

@@ -76,6 +76,8 @@ __global__ void __launch_bounds__(LT_BLOCK) k_path(LtSceneDev sc, LtLaunch L, fl
                                                    LtCounters* gcnt) {
   LT_SMEM_POINTERS(sc)
   (void)tstk;  // the persistent megakernel does not cull (LT_FLAG_CULL selects the wavefront pipeline)
+  const unsigned stkAddr = (unsigned)__cvta_generic_to_shared(stk);
+  const unsigned fifoAddr = (unsigned)__cvta_generic_to_shared(list);
   int px, py;
   bool alive = thread_pixel(L.width, L.height, px, py);
   LtCounters cnt = {0, 0, 0};
@@ -154,9 +156,13 @@ __global__ void __launch_bounds__(LT_BLOCK) k_path(LtSceneDev sc, LtLaunch L, fl
       bool waiting = __any_sync(0xffffffffu, alive && !traversing);
       if (waiting && __popc(active) < L.refillThreshold) break;
       if (traversing) {
-        int n = trav_collect<STATS>(t, sc, stk, list, t.anyHit ? L.batchAnyHit : L.batchClosest, cnt);
-        trav_test<STATS>(t, sc, list, n, pc.epsThr, cnt);
-        traversing = (t.cur != LT_DONE);
+        if (L.batchClosest > 0) {  // leaf-list form: whole batches of box tests, then the recorded triangles
+          int n = trav_collect<STATS>(t, sc, stk, list, t.anyHit ? L.batchAnyHit : L.batchClosest, cnt);
+          trav_test<STATS>(t, sc, list, n, pc.epsThr, cnt);
+          traversing = (t.cur != LT_DONE);
+        } else {  // software-pipelined form (same as the wavefront trace kernel)
+          traversing = !trav_iter_lean<STATS>(t, sc, stkAddr, fifoAddr, pc.epsThr, L.iterNodeSteps, L.iterTriTests, cnt);
+        }
       }
     }
   }

@@ -153,6 +153,8 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_trace(LtSceneDev sc, LtLaunch L
   const int n = B.counts[q];
   const float epsThr = lt_eps(L.kernel);
   const unsigned lane = threadIdx.x & 31u;
+  const unsigned stkAddr = (unsigned)__cvta_generic_to_shared(stk);
+  const unsigned fifoAddr = (unsigned)__cvta_generic_to_shared(list);
   LtCounters cnt = {0, 0, 0};
   const float4* __restrict__ rayO = B.rayO[q];
   const float4* __restrict__ rayD = B.rayD[q];
@@ -204,7 +206,7 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_trace(LtSceneDev sc, LtLaunch L
           trav_step_cull<STATS>(t, sc, stk, tstk, epsThr, cnt);
         finished = t.cur == LT_DONE;
       } else {
-        finished = trav_iter<STATS>(t, sc, stk, list, epsThr, L.iterNodeSteps, L.iterTriTests, cnt);
+        finished = trav_iter_lean<STATS>(t, sc, stkAddr, fifoAddr, epsThr, L.iterNodeSteps, L.iterTriTests, cnt);
       }
       if (finished) {
         B.hits[entry] = make_float4(t.h.t, t.h.u, t.h.v,
