@@ -165,8 +165,12 @@ def run_reference(args, rank, world):
 
 
 def reference_cuda_kernel_rate(sb, w, h):
-    """Kernel-only rate of the reference's own CUDA kernel (NVRTC build of its basic.cu) on this GPU,
-    same buffers, primary rays -- context for the north star's 10x target.  None when oracle/_ref is absent."""
+    """The reference's own CUDA backend on this GPU, primary rays (its only CUDA kernel, basic.cu), same scene
+    and size -- context for the north star's 10x target.  Two numbers, as SURVEY.md 8(d) asks:
+      kernel only : NVRTC build of its basic.cu launched on resident buffers, CUDA events (ltref_time_kernel)
+      as shipped  : wall time of RendererCUDA::render() -- per call it JIT-loads the module, allocates and
+                    uploads five buffers, launches, synchronises and copies the frame back (pageable memory)
+    None when oracle/_ref is absent."""
     import ctypes as C
     lib_path = os.path.join(ROOT, "oracle", "_ref", "libltref.so")
     kpath = os.path.join(ROOT, "oracle", "_ref", "resources", "kernels", "cuda", "basic.cu")
@@ -174,12 +178,12 @@ def reference_cuda_kernel_rate(sb, w, h):
         return None
     try:
         lib = C.CDLL(lib_path)
-        lib.ltref_renderer_cuda_create.restype = C.c_void_p
+        vp, u64 = C.c_void_p, C.c_uint64
+        lib.ltref_renderer_cuda_create.restype = vp
         lib.ltref_time_kernel.restype = C.c_double
-        lib.ltref_time_kernel.argtypes = [C.c_char_p, C.c_char_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64,
-                                          C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64,
-                                          C.c_uint64, C.c_uint64, C.c_uint, C.c_uint, C.c_int, C.c_int, C.c_void_p]
-        lib.ltref_renderer_cuda_create()
+        lib.ltref_time_kernel.argtypes = [C.c_char_p, C.c_char_p, vp, u64, vp, u64, vp, u64, vp, u64, vp, u64, u64, u64,
+                                          C.c_uint, C.c_uint, C.c_int, C.c_int, vp]
+        renderer = lib.ltref_renderer_cuda_create()
         cam = L.make_camera(0, 2.5, -50)
         res = {}
         for bx, by in ((32, 1), (8, 8)):
@@ -189,9 +193,54 @@ def reference_cuda_kernel_rate(sb, w, h):
                                        w, h, 3, bx, by, 3, 10, None)
             if ms > 0:
                 res["block_%dx%d" % (bx, by)] = {"ms": ms, "mrays_s": w * h / ms / 1e3}
+        # as shipped: the reference's own objects (its Model/AS of the Cornell box) through RendererCUDA::render
+        obj = os.path.join(ROOT, "oracle", "_ref", "resources", "models", "cornell_box.obj")
+        if os.path.exists(obj) and len(sb.prims) == 42:
+            for n in ("ltref_model_create", "ltref_as_create", "ltref_camera_create"):
+                getattr(lib, n).restype = vp
+            lib.ltref_model_create.argtypes = [C.c_char_p]
+            lib.ltref_as_create.argtypes = [vp]
+            lib.ltref_camera_create.argtypes = [C.c_float] * 4
+            lib.ltref_render_cuda.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, u64, u64, u64, u64, u64, vp, u64, vp, vp,
+                                              vp]
+            lib.ltref_render_cuda.restype = None
+            model = lib.ltref_model_create(obj.encode())
+            accel = lib.ltref_as_create(model)
+            rcam = lib.ltref_camera_create(0, 2.5, -50, 0)
+            out = np.zeros((h, w, 3), np.float32)
+            times = []
+            for i in range(6):
+                t0 = time.perf_counter()
+                lib.ltref_render_cuda(renderer, kpath.encode(), 0, 0, 0, 0, w, h, 3, out.ctypes.data, out.nbytes, accel,
+                                      model, rcam)
+                times.append((time.perf_counter() - t0) * 1e3)
+            res["render_as_shipped_ms"] = sorted(times[1:])[len(times[1:]) // 2]
         return res or None
     except Exception as e:  # pragma: no cover
         return {"error": str(e)}
+
+
+def this_repo_render_call_ms(w, h):
+    """Wall time of this repo's RendererCUDA::render() for the same call (scene cached after the first call,
+    kernel, D2H into a malloc'ed host buffer)."""
+    from lens_trace_b200 import host
+    cwd = os.getcwd()
+    os.chdir(ROOT)
+    try:
+        cam = host.Camera(0, 2.5, -50, 0)
+        model = host.Model("resources/models/cornell_box.obj")
+        accel = host.AccelerationStructure(model)
+        r = host.Renderer(host.PLATFORM_CUDA)
+        out = np.zeros((h, w, 3), np.float32)
+        times = []
+        for i in range(6):
+            t0 = time.perf_counter()
+            r.render("resources/kernels/cuda/basic.cu", w, h, accel, model, cam, out=out)
+            times.append((time.perf_counter() - t0) * 1e3)
+        r.close(); accel.close(); model.close(); cam.close()
+        return sorted(times[1:])[len(times[1:]) // 2]
+    finally:
+        os.chdir(cwd)
 
 
 def main():
@@ -452,8 +501,10 @@ def main():
                     mine_ms.append(ctx.stats().kernel_ms)
                 mine = sum(mine_ms) / len(mine_ms)
                 line["reference_cuda_backend"] = {
-                    "what": "primary rays (basic.cu), %dx%d, kernel-only, same buffers, same GPU" % (w, h),
+                    "what": "primary rays (basic.cu), %dx%d, same scene, same GPU" % (w, h),
                     "reference_kernel": ref, "this_repo_kernel": {"ms": mine, "mrays_s": w * h / mine / 1e3}}
+                if "render_as_shipped_ms" in ref:
+                    line["reference_cuda_backend"]["this_repo_render_call_ms"] = this_repo_render_call_ms(w, h)
         print(json.dumps(line), flush=True)
 
     scene.release()

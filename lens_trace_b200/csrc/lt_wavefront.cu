@@ -2,7 +2,7 @@
 // global_illumination): the same per-path arithmetic as k_path (lt_kernels.cu), reorganised so that
 // every kernel does one kind of work for every ray that needs it.
 //
-//   generate   camera ray of every (pixel, frame) path of the batch        -> ray queue
+//   primary    round 0 fused: camera ray -> trace -> shade for every (pixel, frame) path of the batch
 //   trace      persistent warps pull rays from the queue; a lane that finishes its ray pulls the
 //              next one at once, so lanes never wait for the longest ray of their warp
 //   shade      one thread per finished ray: consume the hit (shade_step), append the next ray of the
@@ -19,16 +19,18 @@
 #define WF_CHUNK 256  // queue entries a warp claims per global atomic
 
 struct LtWfBuffers {
-  float4* stA;        // nrm.xyz, extW
-  float4* stB;        // diffuse.rgb, bits(hitPrim)
-  float4* stC;        // direct.rgb, bits(depth | stage << 8)
-  float4* stD;        // indirect.rgb, -
+  float4* st;         // 64-byte record per path (two full sectors): [0] nrm.xyz, extW  [1] diffuse.rgb, bits(hitPrim)
+                      //                                             [2] direct.rgb, bits(depth | stage << 8)  [3] indirect.rgb, -
   float4* frameCol;   // running frame colour of the path (the 25-sample blend, or the single sample)
   float4* rayO[2];    // origin.xyz, tStart
   float4* rayD[2];    // direction.xyz, bits((ignore + 1) | anyHit << 31)
   int* rayPath[2];    // path id of the queue entry
   float4* hits;       // t, u, v, bits(prim | hit << 31), indexed like the current queue
-  int* counts;        // [0],[1] queue sizes, [2] trace work counter
+  int* counts;        // [0],[1] queue sizes (front region), [2] trace work counter, [3],[4] sizes of the back
+                      // region of each queue: rays that need the select-chain slab test (a zero direction
+                      // component) are appended from the END of the queue, so they share warps with each other
+                      // and not with the ordinary rays
+  int capacity;       // entries per queue
 };
 
 __device__ __forceinline__ void pixel_of_path(long long path, int pixels, int width, int& px, int& py, int& frameLocal) {
@@ -38,31 +40,46 @@ __device__ __forceinline__ void pixel_of_path(long long path, int pixels, int wi
   px = pixel - py * width;
 }
 
+// queue entry v of [0, front + back): the front region grows from slot 0, the back region from the last slot
+__device__ __forceinline__ int queue_slot(int v, int front, int capacity) {
+  return v < front ? v : capacity - 1 - (v - front);
+}
+
+// does this ray need the select-chain slab test (trav_begin sets LT_EXACT_SLAB for exactly these)?
+__device__ __forceinline__ bool ray_is_degenerate(const Ray& r) {
+  return !(finite3(FRCP(r.dx), FRCP(r.dy), FRCP(r.dz)) && finite3(r.ox, r.oy, r.oz));
+}
+
+// warp-aggregated append of this lane's ray (if emit) to queue `dst`
+__device__ __forceinline__ void queue_append(const LtWfBuffers& B, int dst, bool emit, const Ray& r, float tStart,
+                                             int ignore, bool anyHit, int path, unsigned lane) {
+  bool back = emit && ray_is_degenerate(r);
+  bool front = emit && !back;
+  unsigned fm = __ballot_sync(0xffffffffu, front), bm = __ballot_sync(0xffffffffu, back);
+  int slot = -1;
+  if (fm != 0u) {
+    int base = 0, leader = __ffs(fm) - 1;
+    if ((int)lane == leader) base = atomicAdd(&B.counts[dst], __popc(fm));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (front) slot = base + __popc(fm & ((1u << lane) - 1u));
+  }
+  if (bm != 0u) {
+    int base = 0, leader = __ffs(bm) - 1;
+    if ((int)lane == leader) base = atomicAdd(&B.counts[3 + dst], __popc(bm));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (back) slot = B.capacity - 1 - (base + __popc(bm & ((1u << lane) - 1u)));
+  }
+  if (slot >= 0) {
+    B.rayO[dst][slot] = make_float4(r.ox, r.oy, r.oz, tStart);
+    B.rayD[dst][slot] = make_float4(r.dx, r.dy, r.dz,
+                                    __int_as_float((int)((unsigned)(ignore + 1) | (anyHit ? 0x80000000u : 0u))));
+    B.rayPath[dst][slot] = path;
+  }
+}
+
 __device__ __forceinline__ unsigned sample_index_of(const LtLaunch& L, const PathConsts& pc, int frame, int sample) {
   unsigned fc = L.cam.frameCount + (unsigned)frame * L.frameStride;
   return pc.samplesPerFrame == 25 ? fc * 32u + (unsigned)sample : fc;
-}
-
-// camera rays of all paths of the batch -> queue 0 (entry index = path index)
-__global__ void __launch_bounds__(WF_BLOCK) k_wf_generate(LtLaunch L, LtWfBuffers B, long long nPaths, int pixels) {
-  const PathConsts pc = path_consts(L);
-  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < nPaths;
-       p += (long long)gridDim.x * blockDim.x) {
-    int px, py, fl;
-    pixel_of_path(p, pixels, L.width, px, py, fl);
-    float fx, fy;
-    Ray r = camera_ray(L.cam, px, py, L.width, L.height, fx, fy);
-    B.rayO[0][p] = make_float4(r.ox, r.oy, r.oz, pc.tInit);
-    B.rayD[0][p] = make_float4(r.dx, r.dy, r.dz, __int_as_float(0));  // ignore = -1, closest hit
-    B.rayPath[0][p] = (int)p;
-    B.stC[p] = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(ST_PRIMARY << 8));
-    B.stD[p] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-  }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    B.counts[0] = (int)nPaths;
-    B.counts[1] = 0;
-    B.counts[2] = 0;
-  }
 }
 
 // Round 0 fused: camera ray -> trace -> shade for every path of the batch.  Primary rays are coherent
@@ -112,36 +129,22 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_primary(LtSceneDev sc, LtLaunch
         B.frameCol[p] = make_float4(fc[0], fc[1], fc[2], 0.0f);
       } else {
         emit = true;
-        B.stA[p] = make_float4(ps.nrm[0], ps.nrm[1], ps.nrm[2], ps.extW);
-        B.stB[p] = make_float4(ps.diffuse[0], ps.diffuse[1], ps.diffuse[2], __int_as_float(ps.hitPrim));
-        B.stC[p] = make_float4(ps.direct[0], ps.direct[1], ps.direct[2],
-                               __int_as_float((ps.depth & 0xff) | (ps.stage << 8)));
-        B.stD[p] = make_float4(ps.indirect[0], ps.indirect[1], ps.indirect[2], 0.0f);
+        float4* wr = B.st + 4ll * p;
+        wr[0] = make_float4(ps.nrm[0], ps.nrm[1], ps.nrm[2], ps.extW);
+        wr[1] = make_float4(ps.diffuse[0], ps.diffuse[1], ps.diffuse[2], __int_as_float(ps.hitPrim));
+        wr[2] = make_float4(ps.direct[0], ps.direct[1], ps.direct[2],
+                            __int_as_float((ps.depth & 0xff) | (ps.stage << 8)));
+        wr[3] = make_float4(ps.indirect[0], ps.indirect[1], ps.indirect[2], 0.0f);
       }
     }
-    unsigned em = __ballot_sync(0xffffffffu, emit);
-    if (em != 0u) {
-      int base = 0;
-      int leader = __ffs(em) - 1;
-      if ((int)lane == leader) base = atomicAdd(&B.counts[0], __popc(em));
-      base = __shfl_sync(0xffffffffu, base, leader);
-      if (emit) {
-        int slot = base + __popc(em & ((1u << lane) - 1u));
-        B.rayO[0][slot] = make_float4(t.r.ox, t.r.oy, t.r.oz, tStart);
-        B.rayD[0][slot] = make_float4(t.r.dx, t.r.dy, t.r.dz,
-                                      __int_as_float((int)((unsigned)(ignore + 1) | (anyHit ? 0x80000000u : 0u))));
-        B.rayPath[0][slot] = (int)p;
-      }
-    }
+    queue_append(B, 0, emit, t.r, tStart, ignore, anyHit, (int)p, lane);
   }
   if (STATS) flush_counters(gcnt, cnt);
 }
 
 // zero the queue counters before a batch
 __global__ void k_wf_reset(LtWfBuffers B) {
-  B.counts[0] = 0;
-  B.counts[1] = 0;
-  B.counts[2] = 0;
+  for (int k = 0; k < 5; k++) B.counts[k] = 0;
 }
 
 // persistent trace: lanes pull queue entries through one warp-aggregated atomic per refill
@@ -150,7 +153,8 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_trace(LtSceneDev sc, LtLaunch L
                                                        LtCounters* gcnt) {
   LT_SMEM_POINTERS(sc)
   const bool cull = (L.flags & 2) != 0;  // LT_FLAG_CULL: closest-hit rays skip subtrees behind the current hit
-  const int n = B.counts[q];
+  const int nFront = B.counts[q];
+  const int n = nFront + B.counts[3 + q];  // virtual entries: front region, then the back region
   const float epsThr = lt_eps(L.kernel);
   const unsigned lane = threadIdx.x & 31u;
   const unsigned stkAddr = (unsigned)__cvta_generic_to_shared(stk);
@@ -181,6 +185,7 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_trace(LtSceneDev sc, LtLaunch L
         int idx = chunkNext + __popc(need & ((1u << lane) - 1u));
         chunkNext += __popc(need);
         if (!has && idx < chunkEnd) {
+          idx = queue_slot(idx, nFront, B.capacity);
           float4 o = rayO[idx], d = rayD[idx];
           t.r.ox = o.x; t.r.oy = o.y; t.r.oz = o.z;
           t.r.dx = d.x; t.r.dy = d.y; t.r.dz = d.z;
@@ -222,12 +227,14 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_trace(LtSceneDev sc, LtLaunch L
 __global__ void __launch_bounds__(WF_BLOCK) k_wf_shade(LtSceneDev sc, LtLaunch L, LtWfBuffers B, int q, int pixels,
                                                        int frame0, int sample) {
   const PathConsts pc = path_consts(L);
-  const int n = B.counts[q];
+  const int nFront = B.counts[q];
+  const int n = nFront + B.counts[3 + q];
   const unsigned lane = threadIdx.x & 31u;
   const int rounds = (n + (int)(gridDim.x * blockDim.x) - 1) / (int)(gridDim.x * blockDim.x);
   for (int it = 0; it < rounds; it++) {
     int i = (it * (int)gridDim.x + (int)blockIdx.x) * (int)blockDim.x + (int)threadIdx.x;
     bool valid = i < n;
+    if (valid) i = queue_slot(i, nFront, B.capacity);
     bool emit = false;
     Ray r = {0, 0, 0, 0, 0, 1};
     float tStart = 0.0f;
@@ -244,7 +251,8 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_shade(LtSceneDev sc, LtLaunch L
       h.prim = (int)(hb & 0x7fffffffu);
       h.hit = (int)(hb >> 31);
       PathState ps;
-      float4 a = B.stA[path], b = B.stB[path], c = B.stC[path], dd = B.stD[path];
+      const float4* rec = B.st + 4ll * path;
+      float4 a = rec[0], b = rec[1], c = rec[2], dd = rec[3];
       ps.nrm[0] = a.x; ps.nrm[1] = a.y; ps.nrm[2] = a.z; ps.extW = a.w;
       ps.diffuse[0] = b.x; ps.diffuse[1] = b.y; ps.diffuse[2] = b.z; ps.hitPrim = __float_as_int(b.w);
       ps.direct[0] = c.x; ps.direct[1] = c.y; ps.direct[2] = c.z;
@@ -267,34 +275,22 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_shade(LtSceneDev sc, LtLaunch L
         B.frameCol[path] = make_float4(fc[0], fc[1], fc[2], 0.0f);
       } else {
         emit = true;
-        B.stA[path] = make_float4(ps.nrm[0], ps.nrm[1], ps.nrm[2], ps.extW);
-        B.stB[path] = make_float4(ps.diffuse[0], ps.diffuse[1], ps.diffuse[2], __int_as_float(ps.hitPrim));
-        B.stC[path] = make_float4(ps.direct[0], ps.direct[1], ps.direct[2],
-                                  __int_as_float((ps.depth & 0xff) | (ps.stage << 8)));
-        B.stD[path] = make_float4(ps.indirect[0], ps.indirect[1], ps.indirect[2], 0.0f);
+        float4* wr = B.st + 4ll * path;
+        wr[0] = make_float4(ps.nrm[0], ps.nrm[1], ps.nrm[2], ps.extW);
+        wr[1] = make_float4(ps.diffuse[0], ps.diffuse[1], ps.diffuse[2], __int_as_float(ps.hitPrim));
+        wr[2] = make_float4(ps.direct[0], ps.direct[1], ps.direct[2],
+                            __int_as_float((ps.depth & 0xff) | (ps.stage << 8)));
+        wr[3] = make_float4(ps.indirect[0], ps.indirect[1], ps.indirect[2], 0.0f);
       }
     }
-    // warp-aggregated append to the other queue
-    unsigned em = __ballot_sync(0xffffffffu, emit);
-    if (em != 0u) {
-      int base = 0;
-      int leader = __ffs(em) - 1;
-      if ((int)lane == leader) base = atomicAdd(&B.counts[1 - q], __popc(em));
-      base = __shfl_sync(0xffffffffu, base, leader);
-      if (emit) {
-        int slot = base + __popc(em & ((1u << lane) - 1u));
-        B.rayO[1 - q][slot] = make_float4(r.ox, r.oy, r.oz, tStart);
-        B.rayD[1 - q][slot] = make_float4(r.dx, r.dy, r.dz,
-                                          __int_as_float((int)((unsigned)(ignore + 1) | (anyHit ? 0x80000000u : 0u))));
-        B.rayPath[1 - q][slot] = path;
-      }
-    }
+    queue_append(B, 1 - q, emit, r, tStart, ignore, anyHit, path, lane);
   }
 }
 
 // between rounds: the consumed queue becomes the next output queue
 __global__ void k_wf_swap(LtWfBuffers B, int q) {
   B.counts[q] = 0;
+  B.counts[3 + q] = 0;
   B.counts[2] = 0;
 }
 
@@ -338,10 +334,7 @@ static LtWfBuffers carve(void* workspace, long long nPaths) {
   };
   B.counts = (int*)take(256);
   size_t f4 = sizeof(float4) * (size_t)nPaths;
-  B.stA = (float4*)take(f4);
-  B.stB = (float4*)take(f4);
-  B.stC = (float4*)take(f4);
-  B.stD = (float4*)take(f4);
+  B.st = (float4*)take(4 * f4);
   B.frameCol = (float4*)take(f4);
   for (int k = 0; k < 2; k++) {
     B.rayO[k] = (float4*)take(f4);
@@ -349,6 +342,7 @@ static LtWfBuffers carve(void* workspace, long long nPaths) {
     B.rayPath[k] = (int*)take(sizeof(int) * (size_t)nPaths);
   }
   B.hits = (float4*)take(f4);
+  B.capacity = (int)nPaths;
   return B;
 }
 
