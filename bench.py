@@ -253,6 +253,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true")
     ap.add_argument("--no-cull", action="store_true", help="skip the secondary opt-in culled measurement")
+    ap.add_argument("--no-lbvh", action="store_true", help="skip the secondary opt-in GPU-built LBVH measurement")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -487,6 +488,37 @@ def main():
                 "node_tests_per_ray_actual": sc_.node_tests / max(1, sc_.rays),
                 "tri_tests_per_ray_actual": sc_.tri_tests / max(1, sc_.rays),
                 "speedup_vs_exact": ms_per_step / cms}
+        if world == 1 and not args.no_lbvh and len(sb.prims) >= 2:
+            # OPT-IN device-built LBVH (lt_scene_build_lbvh): a different tree than the reference builder's, so it is
+            # reported beside the headline only.  Same kernels, same workload; picture compared with the headline's.
+            ctx.set_stream(stream.cuda_stream)
+            ctx.render_device(scene, cam, make_step_params(), acc.data_ptr(), sync=True)
+            exact = acc.clone()
+            t0 = time.perf_counter()
+            lscene = ctx.build_lbvh(sb.prims, sb.materials)
+            build_wall_ms = (time.perf_counter() - t0) * 1e3
+            build_dev_ms = ctx.stats().upload_ms
+            times = []
+            for _ in range(max(2, min(args.steps, 3)) + 1):
+                flush.fill_(1.0)
+                c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                c0.record(stream)
+                ctx.render_device(lscene, cam, make_step_params(), acc.data_ptr(), sync=False)
+                c1.record(stream)
+                torch.cuda.synchronize()
+                times.append(c0.elapsed_time(c1))
+            lms = sum(times[1:]) / len(times[1:])
+            differing = int(((acc - exact).abs().amax(dim=-1) > 1e-4 * exact.abs().amax(dim=-1).clamp_min(1e-3)).sum().item())
+            ctx.render_device(lscene, cam, make_step_params(L.FLAG_STATS), acc.data_ptr(), sync=True)
+            sl = ctx.stats()
+            line["lbvh_opt_in"] = {
+                "what": "same workload on an LBVH built on the GPU (ACCELERATION_STRUCTURE_TYPE_LBVH_B200), not the "
+                        "reference builder's tree",
+                "build_ms_device": build_dev_ms, "build_ms_wall": build_wall_ms, "ms_per_step": lms,
+                "value": sl.rays / (lms * 1e-3) / 1e6, "unit": "Mrays/s", "speedup_vs_reference_tree": ms_per_step / lms,
+                "node_tests_per_ray": sl.node_tests / max(1, sl.rays), "tri_tests_per_ray": sl.tri_tests / max(1, sl.rays),
+                "pixels_differing_beyond_1e-4_rel": differing, "pixels": w * h}
+            lscene.release()
         if world == 1 and not args.no_ref_cuda:
             # the reference's CUDA kernel only exists for primary rays (basic.cu); same scene, same size
             ref = reference_cuda_kernel_rate(sb, w, h)

@@ -55,6 +55,8 @@ enum ImageType {
 
 enum AccelerationStructureExplicitType {
   ACCELERATION_STRUCTURE_TYPE_BVH,
+  // --- B200 extension (not in the reference): LBVH built on the GPU (lt_scene_build_lbvh), same flattened layout
+  ACCELERATION_STRUCTURE_TYPE_LBVH_B200 = 100
 };
 
 struct ThreadOrganizationOpenCL {

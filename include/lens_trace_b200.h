@@ -117,6 +117,19 @@ int lt_scene_upload(lt_ctx* ctx, const void* nodes, uint64_t node_bytes, const v
                     const void* light_container, uint64_t light_bytes, lt_scene** out_scene);
 void lt_scene_release(lt_ctx* ctx, lt_scene* scene);
 
+/* --- optional device-side builder (replaces AccelerationStructureExplicit's host build,
+ * src/acceleration_structure_explicit.cpp:3-41,47-137, for large scenes): an LBVH over `primitives` (Primitive[]
+ * in any order, e.g. Model's face order) built on the GPU and emitted in the reference's flattened layout, then
+ * uploaded like lt_scene_upload.  The tree differs from the median-split tree (same results except the winner of
+ * exact ties); lt_scene_download returns the node / ordered-primitive / light buffers it produced (host
+ * pointers, sizes in bytes: 32*(2n-1), 76*n, 260) so the CPU side can hold them. --- */
+int lt_scene_build_lbvh(lt_ctx* ctx, const void* primitives, uint64_t primitive_bytes, const void* materials,
+                        uint64_t material_bytes, lt_scene** out_scene);
+int lt_scene_download(lt_ctx* ctx, lt_scene* scene, void* nodes, uint64_t node_bytes, void* primitives,
+                      uint64_t primitive_bytes, void* light_container);
+/* node and primitive counts of a scene */
+int lt_scene_info(const lt_scene* scene, uint64_t* node_count, uint64_t* primitive_count, int32_t* stack_depth);
+
 /* --- render: replaces cuLaunchKernel + cuCtxSynchronize + cuMemcpyDtoH
  * (src/cuda/renderer_cuda.cpp:113-139).  Synchronous.  host_out (may be NULL) receives
  * width*height*depth floats: the sample (LT_ACCUM_NONE) or the accumulator. --- */

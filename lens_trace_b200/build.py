@@ -41,7 +41,7 @@ def _run(cmd, verbose):
 
 
 def build_b200(force=False, verbose=False, ptxas_verbose=False):
-    srcs = [os.path.join(CSRC, f) for f in ("lt_kernels.cu", "lt_wavefront.cu", "lt_plugin.cu", "lt_capi.cu")]
+    srcs = [os.path.join(CSRC, f) for f in ("lt_kernels.cu", "lt_wavefront.cu", "lt_plugin.cu", "lt_bvh.cu", "lt_capi.cu")]
     deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))] + [
         os.path.join(INC, "lens_trace_b200.h")]
     if not force and not _newer(LIB_B200, deps):

@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "liblt_b200.so")
 SYMBOLS = [
     "lt_api_version", "lt_ctx_create", "lt_ctx_destroy", "lt_last_error", "lt_ctx_set_stream", "lt_scene_upload",
     "lt_scene_release", "lt_render", "lt_render_device", "lt_accum_reset", "lt_accum_read", "lt_primary_hits",
-    "lt_last_stats", "lt_kernel_from_path", "lt_kernel_name", "lt_debug_random", "lt_debug_hemisphere", "lt_plugin_load", "lt_render_plugin", "lt_primary_hits_flags",
+    "lt_last_stats", "lt_kernel_from_path", "lt_kernel_name", "lt_debug_random", "lt_debug_hemisphere", "lt_plugin_load", "lt_render_plugin", "lt_primary_hits_flags", "lt_scene_build_lbvh", "lt_scene_download", "lt_scene_info",
 ]
 
 
@@ -62,6 +62,9 @@ def load():
     lib.lt_ctx_set_stream.argtypes = [C.c_void_p, C.c_void_p]
     lib.lt_scene_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64,
                                     C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
+    lib.lt_scene_build_lbvh.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
+    lib.lt_scene_download.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p]
+    lib.lt_scene_info.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int32)]
     lib.lt_scene_release.argtypes = [C.c_void_p, C.c_void_p]
     lib.lt_scene_release.restype = None
     lib.lt_render.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(RenderParams), C.c_void_p]
@@ -137,6 +140,29 @@ class Context:
                                       scene.lights.ctypes.data, scene.lights.nbytes, C.byref(out))
         self._check(rc, "lt_scene_upload")
         return Scene(self, out)
+
+    def build_lbvh(self, prims, materials):
+        """Device-side LBVH over `prims` (layouts.PRIM array in any order) -> Scene handle"""
+        prims = np.ascontiguousarray(prims, dtype=L.PRIM)
+        materials = np.ascontiguousarray(materials, dtype=L.MATERIAL)
+        out = C.c_void_p()
+        rc = self.lib.lt_scene_build_lbvh(self.h, prims.ctypes.data, prims.nbytes, materials.ctypes.data,
+                                          materials.nbytes, C.byref(out))
+        self._check(rc, "lt_scene_build_lbvh")
+        sc = Scene(self, out)
+        sc.materials = materials.copy()
+        return sc
+
+    def download(self, scene):
+        """The scene's buffers in the reference layouts (layouts.SceneBuffers); materials as uploaded."""
+        nn, np_, sd = C.c_uint64(), C.c_uint64(), C.c_int32()
+        self.lib.lt_scene_info(scene.h, C.byref(nn), C.byref(np_), C.byref(sd))
+        nodes = np.zeros(nn.value, dtype=L.NODE)
+        prims = np.zeros(np_.value, dtype=L.PRIM)
+        lights = np.zeros(1, dtype=L.LIGHTS)
+        self._check(self.lib.lt_scene_download(self.h, scene.h, nodes.ctypes.data, nodes.nbytes, prims.ctypes.data,
+                                               prims.nbytes, lights.ctypes.data), "lt_scene_download")
+        return L.SceneBuffers(nodes, prims, getattr(scene, "materials", np.zeros(0, L.MATERIAL)), lights), sd.value
 
     def render(self, scene, camera, params, want_output=True):
         """Host-buffer path (lt_render): returns float32 [H, W, depth] or None."""

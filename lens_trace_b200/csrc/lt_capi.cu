@@ -163,6 +163,140 @@ extern "C" void lt_scene_release(lt_ctx* ctx, lt_scene* s) {
   delete s;
 }
 
+// Re-flatten on the device (inner-node ranks -> 64-byte child-pair nodes, 48-byte triangles) and fill the
+// device-side scene descriptor.  ev0 must already be recorded on the stream; on failure the scene is released.
+static int finish_scene(lt_ctx* ctx, lt_scene* s, int nNodes, int nPrims, int nMats, const RefNode& root,
+                        int stackDepth, const char* who) {
+  int* dFlags = nullptr;
+  int* dRank = nullptr;
+  void* dTemp = nullptr;
+  int nInner = (nNodes - 1) / 2;  // a full binary tree with one primitive slot per leaf
+  if (nNodes == 1) nInner = 0;
+  size_t tempBytes = lt_scan_temp_bytes(nNodes);
+  cudaError_t e = cudaSuccess;
+  auto A = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+  cudaStream_t st = ctx->stream;
+  A(cudaMalloc(&s->dWide, sizeof(LtWideNode) * (size_t)(nInner > 0 ? nInner : 1)));
+  A(cudaMalloc(&s->dTris, sizeof(LtTri) * (size_t)nPrims));
+  A(cudaMalloc(&dFlags, sizeof(int) * (size_t)nNodes));
+  A(cudaMalloc(&dRank, sizeof(int) * (size_t)nNodes));
+  A(cudaMalloc(&dTemp, tempBytes ? tempBytes : 16));
+  if (e == cudaSuccess) {
+    lt_launch_inner_flags(s->dNodes, nNodes, dFlags, st);
+    lt_launch_exclusive_scan(dTemp, tempBytes, dFlags, dRank, nNodes, st);
+    lt_launch_reflatten(s->dNodes, nNodes, s->dPrims, nPrims, dRank, s->dWide, s->dTris, st);
+    A(cudaGetLastError());
+  }
+  A(cudaEventRecord(ctx->ev1, st));
+  A(cudaStreamSynchronize(st));
+  cudaFree(dFlags);
+  cudaFree(dRank);
+  cudaFree(dTemp);
+  if (e != cudaSuccess) {
+    lt_scene_release(ctx, s);
+    return fail(ctx, LT_ERR_CUDA, std::string(who) + ": " + cudaGetErrorString(e));
+  }
+  cudaEventElapsedTime(&ctx->stats.upload_ms, ctx->ev0, ctx->ev1);
+  LtSceneDev& d = s->dev;
+  d.wnodes = s->dWide;
+  d.tris = s->dTris;
+  d.prims = s->dPrims;
+  d.mats = s->dMats;
+  d.lights = s->dLights;
+  for (int k = 0; k < 3; k++) {
+    d.rootMin[k] = root.boundsMin[k];
+    d.rootMax[k] = root.boundsMax[k];
+  }
+  d.rootRef = root.primitiveCount > 0 ? ~root.offset : 0;  // inner root is wide node 0
+  d.rootCount = root.primitiveCount;
+  d.stackDepth = stackDepth;
+  d.nodeCount = nNodes;
+  d.primCount = nPrims;
+  d.matCount = nMats;
+  return LT_OK;
+}
+
+extern "C" int lt_scene_build_lbvh(lt_ctx* ctx, const void* primitives, uint64_t primitive_bytes, const void* materials,
+                                   uint64_t material_bytes, lt_scene** out_scene) {
+  if (!ctx) return fail(nullptr, LT_ERR_INVALID, "lt_scene_build_lbvh: ctx is NULL");
+  if (!out_scene || !primitives || !materials) return fail(ctx, LT_ERR_INVALID, "lt_scene_build_lbvh: NULL argument");
+  *out_scene = nullptr;
+  if (primitive_bytes == 0 || primitive_bytes % sizeof(RefPrim) || material_bytes == 0 ||
+      material_bytes % sizeof(RefMaterial))
+    return fail(ctx, LT_ERR_INVALID, "lt_scene_build_lbvh: buffer size is not a multiple of the reference record size");
+  uint64_t nPrims = primitive_bytes / sizeof(RefPrim), nMats = material_bytes / sizeof(RefMaterial);
+  if (nPrims < 2) return fail(ctx, LT_ERR_UNSUPPORTED, "lt_scene_build_lbvh: needs at least two primitives");
+  if (nPrims > 0x3fffffffull) return fail(ctx, LT_ERR_INVALID, "lt_scene_build_lbvh: too many primitives");
+  const RefPrim* hPrims = (const RefPrim*)primitives;
+  for (uint64_t i = 0; i < nPrims; i++)
+    if (hPrims[i].materialIndex < 0 || (uint64_t)hPrims[i].materialIndex >= nMats)
+      return fail(ctx, LT_ERR_INVALID, "lt_scene_build_lbvh: primitive materialIndex out of range");
+  CK(cudaSetDevice(ctx->device));
+  int n = (int)nPrims, nNodes = 2 * n - 1;
+  lt_scene* s = new lt_scene();
+  RefPrim* dInput = nullptr;
+  void* scratch = nullptr;
+  size_t scratchBytes = lt_bvh_scratch_bytes(n);
+  cudaError_t e = cudaSuccess;
+  auto A = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+  A(cudaMalloc(&s->dNodes, sizeof(RefNode) * (size_t)nNodes));
+  A(cudaMalloc(&s->dPrims, primitive_bytes));
+  A(cudaMalloc(&s->dMats, material_bytes));
+  A(cudaMalloc(&s->dLights, sizeof(RefLights)));
+  A(cudaMalloc(&dInput, primitive_bytes));
+  A(cudaMalloc(&scratch, scratchBytes));
+  cudaStream_t st = ctx->stream;
+  A(cudaEventRecord(ctx->ev0, st));
+  A(cudaMemcpyAsync(dInput, primitives, primitive_bytes, cudaMemcpyHostToDevice, st));
+  A(cudaMemcpyAsync(s->dMats, materials, material_bytes, cudaMemcpyHostToDevice, st));
+  int maxDepth = 0, launches = -1;
+  if (e == cudaSuccess)
+    launches = lt_launch_bvh_build(dInput, n, s->dMats, (int)nMats, s->dNodes, s->dPrims, s->dLights, scratch, scratchBytes,
+                                   &maxDepth, st);
+  RefNode root;
+  memset(&root, 0, sizeof root);
+  if (e == cudaSuccess && launches >= 0) A(cudaMemcpy(&root, s->dNodes, sizeof root, cudaMemcpyDeviceToHost));
+  cudaFree(dInput);
+  cudaFree(scratch);
+  if (e != cudaSuccess || launches < 0) {
+    lt_scene_release(ctx, s);
+    return fail(ctx, LT_ERR_CUDA, std::string("lt_scene_build_lbvh: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "build failed"));
+  }
+  if (maxDepth > 64) {
+    lt_scene_release(ctx, s);
+    return fail(ctx, LT_ERR_UNSUPPORTED, "lt_scene_build_lbvh: tree deeper than 64 (too many coincident centroids); use the host builder");
+  }
+  int rc = finish_scene(ctx, s, nNodes, n, (int)nMats, root, maxDepth, "lt_scene_build_lbvh");
+  if (rc != LT_OK) return rc;
+  *out_scene = s;
+  return LT_OK;
+}
+
+extern "C" int lt_scene_download(lt_ctx* ctx, lt_scene* scene, void* nodes, uint64_t node_bytes, void* primitives,
+                                 uint64_t primitive_bytes, void* light_container) {
+  if (!ctx || !scene) return fail(ctx, LT_ERR_INVALID, "lt_scene_download: NULL argument");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (nodes) {
+    if (node_bytes != sizeof(RefNode) * (uint64_t)scene->dev.nodeCount) return fail(ctx, LT_ERR_INVALID, "lt_scene_download: node_bytes mismatch");
+    CK(cudaMemcpy(nodes, scene->dNodes, node_bytes, cudaMemcpyDeviceToHost));
+  }
+  if (primitives) {
+    if (primitive_bytes != sizeof(RefPrim) * (uint64_t)scene->dev.primCount) return fail(ctx, LT_ERR_INVALID, "lt_scene_download: primitive_bytes mismatch");
+    CK(cudaMemcpy(primitives, scene->dPrims, primitive_bytes, cudaMemcpyDeviceToHost));
+  }
+  if (light_container) CK(cudaMemcpy(light_container, scene->dLights, sizeof(RefLights), cudaMemcpyDeviceToHost));
+  return LT_OK;
+}
+
+extern "C" int lt_scene_info(const lt_scene* scene, uint64_t* node_count, uint64_t* primitive_count, int32_t* stack_depth) {
+  if (!scene) return LT_ERR_INVALID;
+  if (node_count) *node_count = (uint64_t)scene->dev.nodeCount;
+  if (primitive_count) *primitive_count = (uint64_t)scene->dev.primCount;
+  if (stack_depth) *stack_depth = scene->dev.stackDepth;
+  return LT_OK;
+}
+
 extern "C" int lt_scene_upload(lt_ctx* ctx, const void* nodes, uint64_t node_bytes, const void* primitives,
                                uint64_t primitive_bytes, const void* materials, uint64_t material_bytes,
                                const void* light_container, uint64_t light_bytes, lt_scene** out_scene) {
@@ -198,62 +332,24 @@ extern "C" int lt_scene_upload(lt_ctx* ctx, const void* nodes, uint64_t node_byt
 
   CK(cudaSetDevice(ctx->device));
   lt_scene* s = new lt_scene();
-  int* dFlags = nullptr;
-  int* dRank = nullptr;
-  void* dTemp = nullptr;
-  int nInner = 0;
-  for (uint64_t i = 0; i < nNodes; i++) nInner += hNodes[i].primitiveCount == 0;
-  size_t tempBytes = lt_scan_temp_bytes((int)nNodes);
   cudaError_t e = cudaSuccess;
   auto A = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
   A(cudaMalloc(&s->dNodes, node_bytes));
   A(cudaMalloc(&s->dPrims, primitive_bytes));
   A(cudaMalloc(&s->dMats, material_bytes ? material_bytes : sizeof(RefMaterial)));
   A(cudaMalloc(&s->dLights, sizeof(RefLights)));
-  A(cudaMalloc(&s->dWide, sizeof(LtWideNode) * (size_t)(nInner > 0 ? nInner : 1)));
-  A(cudaMalloc(&s->dTris, sizeof(LtTri) * nPrims));
-  A(cudaMalloc(&dFlags, sizeof(int) * nNodes));
-  A(cudaMalloc(&dRank, sizeof(int) * nNodes));
-  A(cudaMalloc(&dTemp, tempBytes ? tempBytes : 16));
   cudaStream_t st = ctx->stream;
   A(cudaEventRecord(ctx->ev0, st));
   A(cudaMemcpyAsync(s->dNodes, nodes, node_bytes, cudaMemcpyHostToDevice, st));
   A(cudaMemcpyAsync(s->dPrims, primitives, primitive_bytes, cudaMemcpyHostToDevice, st));
   if (material_bytes) A(cudaMemcpyAsync(s->dMats, materials, material_bytes, cudaMemcpyHostToDevice, st));
   A(cudaMemcpyAsync(s->dLights, light_container, sizeof(RefLights), cudaMemcpyHostToDevice, st));
-  if (e == cudaSuccess) {
-    lt_launch_inner_flags(s->dNodes, (int)nNodes, dFlags, st);
-    lt_launch_exclusive_scan(dTemp, tempBytes, dFlags, dRank, (int)nNodes, st);
-    lt_launch_reflatten(s->dNodes, (int)nNodes, s->dPrims, (int)nPrims, dRank, s->dWide, s->dTris, st);
-    A(cudaGetLastError());
-  }
-  A(cudaEventRecord(ctx->ev1, st));
-  A(cudaStreamSynchronize(st));
-  cudaFree(dFlags);
-  cudaFree(dRank);
-  cudaFree(dTemp);
   if (e != cudaSuccess) {
     lt_scene_release(ctx, s);
     return fail(ctx, LT_ERR_CUDA, std::string("lt_scene_upload: ") + cudaGetErrorString(e));
   }
-  cudaEventElapsedTime(&ctx->stats.upload_ms, ctx->ev0, ctx->ev1);
-
-  LtSceneDev& d = s->dev;
-  d.wnodes = s->dWide;
-  d.tris = s->dTris;
-  d.prims = s->dPrims;
-  d.mats = s->dMats;
-  d.lights = s->dLights;
-  for (int k = 0; k < 3; k++) {
-    d.rootMin[k] = hNodes[0].boundsMin[k];
-    d.rootMax[k] = hNodes[0].boundsMax[k];
-  }
-  d.rootRef = hNodes[0].primitiveCount > 0 ? ~hNodes[0].offset : 0;  // inner root is wide node 0
-  d.rootCount = hNodes[0].primitiveCount;
-  d.stackDepth = stackDepth;
-  d.nodeCount = (int)nNodes;
-  d.primCount = (int)nPrims;
-  d.matCount = (int)nMats;
+  int rc = finish_scene(ctx, s, (int)nNodes, (int)nPrims, (int)nMats, hNodes[0], stackDepth, "lt_scene_upload");
+  if (rc != LT_OK) return rc;
   *out_scene = s;
   return LT_OK;
 }

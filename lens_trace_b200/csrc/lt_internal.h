@@ -131,3 +131,9 @@ void lt_plugin_free(LtPlugin* p);
 int lt_plugin_launch(LtPlugin* p, int kernelMode, const void* dNodes, const void* dPrims, const void* dMats,
                      const void* dLights, const void* dCamera, float* dOut, int width, int height, int depth, int bx,
                      int by, cudaStream_t stream, std::string* err);
+
+// device-side LBVH construction in the reference's flattened layout (lt_bvh.cu)
+size_t lt_bvh_scratch_bytes(int n);
+int lt_launch_bvh_build(const RefPrim* dPrims, int n, const RefMaterial* dMats, int matCount, RefNode* dNodes,
+                        RefPrim* dOrderedPrims, RefLights* dLights, void* scratch, size_t scratchBytes, int* outMaxDepth,
+                        cudaStream_t stream);

@@ -16,7 +16,7 @@ PLATFORM_CUDA = 1
 
 SYMBOLS = [
     "lth_model_create", "lth_model_destroy", "lth_model_ok", "lth_model_primitive_count", "lth_model_material_buffer",
-    "lth_model_material_bytes", "lth_as_create", "lth_as_destroy", "lth_as_node_buffer", "lth_as_node_bytes",
+    "lth_model_material_bytes", "lth_as_create", "lth_as_create_typed", "lth_as_destroy", "lth_as_node_buffer", "lth_as_node_bytes",
     "lth_as_primitive_buffer", "lth_as_primitive_bytes", "lth_as_light_buffer", "lth_as_light_bytes",
     "lth_camera_create", "lth_camera_destroy", "lth_camera_buffer", "lth_camera_set_frame_count",
     "lth_camera_increment_frame_count", "lth_camera_set_position", "lth_camera_set_rotation", "lth_renderer_create",
@@ -54,10 +54,12 @@ def load():
         getattr(lib, name).restype = u64
     lib.lth_model_create.argtypes = [C.c_char_p]
     for name in ("lth_model_destroy", "lth_model_ok", "lth_model_primitive_count", "lth_model_material_buffer",
-                 "lth_model_material_bytes", "lth_as_create", "lth_as_destroy", "lth_as_node_buffer",
+                 "lth_model_material_bytes", "lth_as_create", "lth_as_create_typed", "lth_as_destroy", "lth_as_node_buffer",
                  "lth_as_node_bytes", "lth_as_primitive_buffer", "lth_as_primitive_bytes", "lth_as_light_buffer",
                  "lth_as_light_bytes", "lth_camera_destroy", "lth_camera_buffer", "lth_camera_increment_frame_count"):
         getattr(lib, name).argtypes = [vp]
+    lib.lth_as_create_typed.restype = vp
+    lib.lth_as_create_typed.argtypes = [vp, C.c_int]
     lib.lth_camera_create.argtypes = [C.c_float] * 4
     lib.lth_camera_set_frame_count.argtypes = [vp, C.c_uint32]
     lib.lth_camera_set_position.argtypes = [vp, C.c_float, C.c_float, C.c_float]
@@ -98,10 +100,13 @@ class Model:
 
 
 class AccelerationStructure:
-    def __init__(self, model):
+    HOST_MEDIAN_SPLIT = 0
+    GPU_LBVH = 100
+
+    def __init__(self, model, kind=0):
         self.lib = load()
         self.model = model
-        self.h = self.lib.lth_as_create(model.h)
+        self.h = self.lib.lth_as_create_typed(model.h, kind)
 
     def buffers(self):
         """Copies of the flat buffers as layouts.SceneBuffers."""

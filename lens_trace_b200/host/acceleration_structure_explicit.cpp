@@ -10,6 +10,8 @@
 #include <float.h>
 #include <stdio.h>
 
+#include "lens_trace_b200.h"
+
 namespace {
 
 struct BuildItem {
@@ -97,6 +99,36 @@ AccelerationStructureExplicit::AccelerationStructureExplicit(
   const size_t materialCount = pModel->getMaterialBufferSize() / sizeof(Material);
   memset(&lightContainer, 0, sizeof lightContainer);
   if (infos.empty()) return;
+
+  // opt-in: build on the GPU (Morton-order LBVH, lens_trace_b200/csrc/lt_bvh.cu) and keep the result in the
+  // same host-side buffers; if no device is usable the host median-split build below is used instead
+  if (accelerationStructureExplicitProperties.accelerationStructureExplicitType == ACCELERATION_STRUCTURE_TYPE_LBVH_B200 &&
+      infos.size() >= 2) {
+    std::vector<Primitive> input(infos.size());
+    for (size_t x = 0; x < infos.size(); x++) {
+      memcpy(input[x].positionA, infos[x].positionA, sizeof(float) * 18);  // positions + normals are contiguous
+      input[x].materialIndex = infos[x].materialIndex;
+    }
+    lt_ctx* ctx = nullptr;
+    lt_scene* scene = nullptr;
+    bool ok = lt_ctx_create(0, &ctx) == LT_OK &&
+              lt_scene_build_lbvh(ctx, input.data(), input.size() * sizeof(Primitive), materials,
+                                  materialCount * sizeof(Material), &scene) == LT_OK;
+    if (ok) {
+      linearNodes.resize(2 * infos.size() - 1);
+      orderedPrimitives.resize(infos.size());
+      ok = lt_scene_download(ctx, scene, linearNodes.data(), linearNodes.size() * sizeof(LinearBVHNode),
+                             orderedPrimitives.data(), orderedPrimitives.size() * sizeof(Primitive),
+                             &lightContainer) == LT_OK;
+    }
+    if (!ok) printf("WARNING: GPU BVH build unavailable (%s); using the host builder\n", lt_last_error(ctx));
+    if (scene) lt_scene_release(ctx, scene);
+    if (ctx) lt_ctx_destroy(ctx);
+    if (ok) return;
+    linearNodes.clear();
+    orderedPrimitives.clear();
+    memset(&lightContainer, 0, sizeof lightContainer);
+  }
 
   Builder b(infos, linearNodes);
   b.build(0, (int)infos.size());

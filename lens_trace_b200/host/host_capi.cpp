@@ -23,6 +23,14 @@ void* lth_as_create(void* model) {
   props.pModel = model;
   return new AccelerationStructureExplicit(props);
 }
+void* lth_as_create_typed(void* model, int type) {
+  AccelerationStructureExplicitProperties props = {};
+  props.sType = STRUCTURE_TYPE_ACCELERATION_STRUCTURE_PROPERTIES;
+  props.pNext = NULL;
+  props.accelerationStructureExplicitType = (AccelerationStructureExplicitType)type;
+  props.pModel = model;
+  return new AccelerationStructureExplicit(props);
+}
 void lth_as_destroy(void* as) { delete (AccelerationStructureExplicit*)as; }
 void* lth_as_node_buffer(void* as) { return ((AccelerationStructureExplicit*)as)->getNodeBuffer(); }
 uint64_t lth_as_node_bytes(void* as) { return ((AccelerationStructureExplicit*)as)->getNodeBufferSize(); }

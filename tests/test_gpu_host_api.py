@@ -248,3 +248,18 @@ def test_headless_examples_build_and_run(tmp_path):
         r = subprocess.run([os.path.join(util.ROOT, "examples", "bin", exe)] + args, cwd=util.ROOT, capture_output=True,
                            text=True, timeout=300)
         assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_acceleration_structure_gpu_lbvh_option():
+    """AccelerationStructureExplicit with ACCELERATION_STRUCTURE_TYPE_LBVH_B200: built on the GPU, held on the host
+    in the reference layout, rendered through RendererCUDA like any other."""
+    os.chdir(util.ROOT)
+    cam = host.Camera(0, 2.5, -50, 0)
+    model = host.Model("resources/models/cornell_box.obj")
+    accel = host.AccelerationStructure(model, host.AccelerationStructure.GPU_LBVH)
+    sb = accel.buffers()
+    assert len(sb.nodes) == 83 and sb.lights["count"][0] == 2
+    r = host.Renderer(host.PLATFORM_CUDA)
+    got = r.render("resources/kernels/cuda/basic.cu", 128, 96, accel, model, cam)
+    util.assert_bit_equal(got, O.render(L.KERNEL_BASIC_CU, sb, util.default_camera(), 128, 96))
+    r.close(); accel.close(); model.close(); cam.close()

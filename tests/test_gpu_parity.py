@@ -288,3 +288,71 @@ def test_bad_arguments_are_errors(ctx):
     bad.nodes["offset"][0] = 10 ** 6
     with pytest.raises(capi.LtError):
         ctx.upload(bad)
+
+
+def _model_prims(name_or_path):
+    """Primitive records in Model (file) order, i.e. NOT yet ordered by any builder."""
+    from lens_trace_b200 import host
+    import os
+    path = name_or_path if os.path.exists(name_or_path) else os.path.join(util.MODELS, name_or_path + ".obj")
+    sb = host.load_scene_buffers(path)
+    rng = np.random.default_rng(5)
+    perm = rng.permutation(len(sb.prims))
+    return sb.prims[perm].copy(), sb.materials.copy(), sb
+
+
+@pytest.mark.parametrize("name", ["cornell_box", "cornell_box_lens", "green_wall"])
+def test_gpu_lbvh_builder(ctx, name):
+    """lt_scene_build_lbvh: a valid tree in the reference layout (every primitive in exactly one leaf, boxes
+    contain children, DFS order), traversed identically by the kernels and by the CPU oracle, and giving the
+    same picture as the median-split tree."""
+    from test_host import _check_tree
+    prims, mats, median = _model_prims(name)
+    sc = ctx.build_lbvh(prims, mats)
+    sb, depth = ctx.download(sc)
+    assert len(sb.nodes) == 2 * len(prims) - 1 and 1 <= depth <= 64
+    _check_tree(sb)
+    assert sorted(p.tobytes() for p in sb.prims) == sorted(p.tobytes() for p in prims)
+    n = sb.lights["count"][0]
+    assert n == median.lights["count"][0]
+    for p in sb.lights["prims"][0][:n]:
+        assert sb.materials["emission"][sb.prims["mat"][p]].max() > 0
+    cam = util.default_camera(0.03, 1)
+    ids, hit, tuv = ctx.primary_hits(sc, cam, L.KERNEL_BASIC_CU, 200, 150)
+    oids, ohit, otuv, _ = O.primary_hits(0, sb, cam, 200, 150)
+    np.testing.assert_array_equal(hit, ohit)
+    np.testing.assert_array_equal(ids, oids)
+    util.assert_bit_equal(tuv, otuv, "LBVH: kernels vs oracle on the same buffers")
+    got = ctx.render(sc, cam, capi.make_params(L.KERNEL_GI, 160, 120, max_ray_depth=4))
+    want = O.render(L.KERNEL_GI, sb, cam, 160, 120, max_ray_depth=4, threads=0)
+    assert_images_match(got, want, "LBVH GI vs oracle", max_outliers=3)
+    # same picture as the median-split tree for the deterministic kernel (ties at shared edges may pick the
+    # other of two coplanar triangles, which has the same material here)
+    _, msc = gpu_scene(ctx, name)
+    a = ctx.render(sc, cam, capi.make_params(L.KERNEL_BASIC_CU, 200, 150))
+    b = ctx.render(msc, cam, capi.make_params(L.KERNEL_BASIC_CU, 200, 150))
+    assert (np.abs(a - b).max(axis=-1) > 0).mean() < 0.002
+    sc.release()
+
+
+def test_gpu_lbvh_builder_large(ctx, tmp_path):
+    from lens_trace_b200 import host
+    from test_host import _check_tree
+    p = str(tmp_path / "synth.obj")
+    host.write_synthetic_scene(p, 200, 0x5EED)  # 80 012 triangles (exercises the parallel light selection)
+    prims, mats, median = _model_prims(p)
+    sc = ctx.build_lbvh(prims, mats)
+    sb, depth = ctx.download(sc)
+    _check_tree(sb)
+    assert sb.lights["count"][0] == 2 and depth <= 64
+    cam = util.default_camera()
+    ids, hit, tuv = ctx.primary_hits(sc, cam, L.KERNEL_GI, 320, 180)
+    oids, ohit, otuv, _ = O.primary_hits(2, sb, cam, 320, 180)
+    np.testing.assert_array_equal(ids, oids)
+    util.assert_bit_equal(tuv, otuv)
+    msc = ctx.upload(median)
+    a = ctx.primary_hits(msc, cam, L.KERNEL_GI, 320, 180)
+    assert (a[1] == hit).all()  # same hit mask as the median-split tree
+    np.testing.assert_allclose(a[2][..., 0][hit == 1], tuv[..., 0][hit == 1], rtol=1e-5)
+    msc.release()
+    sc.release()
