@@ -562,7 +562,7 @@ extern "C" int lt_render_plugin(lt_ctx* ctx, lt_scene* scene, const void* camera
   CK(cudaMemcpyAsync(ctx->dCamera, camera28, sizeof(RefCamera), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
   std::string err;
-  if (lt_plugin_launch(ctx->plugins[plugin_id], kernel_mode ? 1 : 0, scene->dNodes, scene->dPrims, scene->dMats,
+  if (lt_plugin_launch(ctx->plugins[plugin_id], kernel_mode ? 1 : 0, &scene->dev, scene->dNodes, scene->dPrims, scene->dMats,
                        scene->dLights, ctx->dCamera, ctx->dOut, width, height, depth, block_x, block_y, ctx->stream,
                        &err) != 0)
     return fail(ctx, LT_ERR_CUDA, "lt_render_plugin: " + err);

@@ -4,80 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-// ---- reference layouts (as uploaded by the caller) ----
-struct RefNode {  // include/lens_trace/acceleration_structure_explicit.h:20-32 (32 B)
-  float boundsMin[3];
-  float boundsMax[3];
-  int32_t offset;  // primitivesOffset | secondChildOffset
-  uint16_t primitiveCount;
-  uint8_t axis;
-  uint8_t pad;
-};
-static_assert(sizeof(RefNode) == 32, "LinearBVHNode is 32 bytes");
-
-struct RefPrim {  // include/lens_trace/acceleration_structure_explicit.h:34-42 (76 B)
-  float a[3], b[3], c[3];
-  float na[3], nb[3], nc[3];
-  int32_t materialIndex;
-};
-static_assert(sizeof(RefPrim) == 76, "Primitive is 76 bytes");
-
-struct RefMaterial {  // include/lens_trace/model.h:26-31 (32 B)
-  float diffuse[3];
-  float ior;
-  float dissolve;
-  float emission[3];
-};
-static_assert(sizeof(RefMaterial) == 32, "Material is 32 bytes");
-
-struct RefLights {  // include/lens_trace/acceleration_structure_explicit.h:44-47 (260 B)
-  uint32_t count;
-  uint32_t primitives[64];
-};
-
-struct RefCamera {  // src/camera.cpp:14-19 (28 B)
-  float position[3];
-  float yaw, pitch, roll;
-  uint32_t frameCount;
-};
-static_assert(sizeof(RefCamera) == 28, "camera buffer is 28 bytes");
-
-// ---- re-flattened device layouts ----
-// One 64-byte record per INNER reference node, holding the boxes of both children so that one
-// dependent round trip tests two reference nodes.  Child reference: >= 0 -> index of the child's
-// own LtWideNode; < 0 -> ~primitivesOffset of a leaf child.  Four 128-bit loads.
-struct __align__(16) LtWideNode {
-  float4 bx;   // Lmin.x Lmax.x Rmin.x Rmax.x   (L = reference node i+1, R = secondChildOffset)
-  float4 by;   // Lmin.y Lmax.y Rmin.y Rmax.y
-  float4 bz;   // Lmin.z Lmax.z Rmin.z Rmax.z
-  int4 meta;   // Lref, Rref, axis, (Lcount | Rcount << 16)  (leaf primitiveCount, stats only)
-};
-static_assert(sizeof(LtWideNode) == 64, "wide node is 64 bytes");
-
-// 48-byte triangle record for the intersection test: A, e1 = B - A, e2 = C - A (the same IEEE
-// subtractions basic.cu:100-101 performs per test, done once at upload).  Three 128-bit loads.
-struct __align__(16) LtTri {
-  float4 q0;  // A.x A.y A.z e1.x
-  float4 q1;  // e1.y e1.z e2.x e2.y
-  float4 q2;  // e2.z bits(materialIndex) 0 0
-};
-static_assert(sizeof(LtTri) == 48, "triangle record is 48 bytes");
-
-#define LT_DONE ((int)0x80000000)  // traversal sentinel (== ~0x7fffffff, never a primitive)
-
-struct LtSceneDev {
-  const LtWideNode* wnodes;
-  const LtTri* tris;
-  const RefPrim* prims;       // original 76-byte records, read only when shading a hit
-  const RefMaterial* mats;
-  const RefLights* lights;
-  float rootMin[3];
-  float rootMax[3];
-  int rootRef;                // child reference of the root (leaf root -> ~primitivesOffset)
-  int rootCount;              // primitiveCount of a leaf root (stats only)
-  int stackDepth;             // entries a traversal stack needs (tree depth), <= 64
-  int nodeCount, primCount, matCount;
-};
+#include "lens_trace_b200_device.cuh"  // buffer layouts shared with plug-in kernels
 
 struct LtLaunch {
   int kernel;        // lt_kernel
@@ -128,9 +55,9 @@ int lt_launch_render_wavefront(const LtSceneDev& sc, const LtLaunch& L, float* d
 struct LtPlugin;
 LtPlugin* lt_plugin_compile(const char* path, std::string* err);
 void lt_plugin_free(LtPlugin* p);
-int lt_plugin_launch(LtPlugin* p, int kernelMode, const void* dNodes, const void* dPrims, const void* dMats,
-                     const void* dLights, const void* dCamera, float* dOut, int width, int height, int depth, int bx,
-                     int by, cudaStream_t stream, std::string* err);
+int lt_plugin_launch(LtPlugin* p, int kernelMode, const LtSceneDev* sceneDev, const void* dNodes, const void* dPrims,
+                     const void* dMats, const void* dLights, const void* dCamera, float* dOut, int width, int height,
+                     int depth, int bx, int by, cudaStream_t stream, std::string* err);
 
 // device-side LBVH construction in the reference's flattened layout (lt_bvh.cu)
 size_t lt_bvh_scratch_bytes(int n);

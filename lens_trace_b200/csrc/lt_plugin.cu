@@ -35,6 +35,8 @@ struct Api {
   CUresult (*moduleGetFunction)(CUfunction*, CUmodule, const char*);
   CUresult (*launchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream,
                            void**, void**);
+  CUresult (*moduleGetGlobal)(CUdeviceptr*, size_t*, CUmodule, const char*);
+  CUresult (*memcpyHtoDAsync)(CUdeviceptr, const void*, size_t, CUstream);
 };
 
 Api g_api;
@@ -65,7 +67,8 @@ bool load_api() {
          sym(rtc, "nvrtcGetCUBINSize", a.getCUBINSize, a.why) && sym(rtc, "nvrtcGetCUBIN", a.getCUBIN, a.why) &&
          sym(rtc, "nvrtcDestroyProgram", a.destroyProgram, a.why) && sym(drv, "cuModuleLoadData", a.moduleLoadData, a.why) &&
          sym(drv, "cuModuleUnload", a.moduleUnload, a.why) && sym(drv, "cuModuleGetFunction", a.moduleGetFunction, a.why) &&
-         sym(drv, "cuLaunchKernel", a.launchKernel, a.why);
+         sym(drv, "cuLaunchKernel", a.launchKernel, a.why) && sym(drv, "cuModuleGetGlobal_v2", a.moduleGetGlobal, a.why) &&
+         sym(drv, "cuMemcpyHtoDAsync_v2", a.memcpyHtoDAsync, a.why);
   return a.ok;
 }
 
@@ -75,7 +78,13 @@ struct LtPlugin {
   std::string path;
   CUmodule module = nullptr;
   CUfunction linear = nullptr, tile = nullptr;
+  CUdeviceptr sceneSymbol = 0;  // address of the plug-in's `lt_scene` constant, 0 if it does not use the device API
 };
+
+// text of include/lens_trace_b200_device.cuh, handed to NVRTC as the header "lens_trace_b200_device.cuh"
+static const char* kDeviceApiHeader =
+#include "lt_device_api_embed.inc"
+    ;
 
 // Compiles `path`; on failure returns nullptr and the compiler log / reason in `err`.
 LtPlugin* lt_plugin_compile(const char* path, std::string* err) {
@@ -94,7 +103,9 @@ LtPlugin* lt_plugin_compile(const char* path, std::string* err) {
   while ((n = fread(buf, 1, sizeof buf, f)) > 0) src.append(buf, n);
   fclose(f);
   nvrtcProgram prog;
-  if (g_api.createProgram(&prog, src.c_str(), path, 0, nullptr, nullptr) != NVRTC_SUCCESS) {
+  const char* headerNames[] = {"lens_trace_b200_device.cuh"};
+  const char* headerTexts[] = {kDeviceApiHeader};
+  if (g_api.createProgram(&prog, src.c_str(), path, 1, headerTexts, headerNames) != NVRTC_SUCCESS) {
     *err = "nvrtcCreateProgram failed";
     return nullptr;
   }
@@ -123,6 +134,12 @@ LtPlugin* lt_plugin_compile(const char* path, std::string* err) {
   }
   g_api.moduleGetFunction(&p->linear, p->module, "linearKernel");
   g_api.moduleGetFunction(&p->tile, p->module, "tileKernel");
+  {
+    size_t bytes = 0;
+    CUdeviceptr addr = 0;
+    if (g_api.moduleGetGlobal(&addr, &bytes, p->module, "lt_scene") == CUDA_SUCCESS && bytes == sizeof(LtSceneDev))
+      p->sceneSymbol = addr;
+  }
   if (!p->linear && !p->tile) {
     *err = std::string(path) + " exports neither linearKernel nor tileKernel (extern \"C\" __global__)";
     g_api.moduleUnload(p->module);
@@ -140,10 +157,15 @@ void lt_plugin_free(LtPlugin* p) {
 
 // Launch shape of the reference: grid = ceil(W/bx) x ceil(H/by), block = bx x by (32x1 for MAX_FIT,
 // src/cuda/renderer_cuda.cpp:74-88).  Returns 0, or -1 with `err` set.
-int lt_plugin_launch(LtPlugin* p, int kernelMode, const void* dNodes, const void* dPrims, const void* dMats,
-                     const void* dLights, const void* dCamera, float* dOut, int width, int height, int depth, int bx,
-                     int by, cudaStream_t stream, std::string* err) {
+int lt_plugin_launch(LtPlugin* p, int kernelMode, const LtSceneDev* sceneDev, const void* dNodes, const void* dPrims,
+                     const void* dMats, const void* dLights, const void* dCamera, float* dOut, int width, int height,
+                     int depth, int bx, int by, cudaStream_t stream, std::string* err) {
   CUfunction fn = kernelMode ? p->tile : p->linear;
+  if (p->sceneSymbol && sceneDev &&
+      g_api.memcpyHtoDAsync(p->sceneSymbol, sceneDev, sizeof(LtSceneDev), (CUstream)stream) != CUDA_SUCCESS) {
+    *err = "cannot set lt_scene of plug-in " + p->path;
+    return -1;
+  }
   if (!fn) {
     *err = p->path + (kernelMode ? " has no tileKernel" : " has no linearKernel");
     return -1;

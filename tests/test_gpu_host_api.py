@@ -263,3 +263,25 @@ def test_acceleration_structure_gpu_lbvh_option():
     got = r.render("resources/kernels/cuda/basic.cu", 128, 96, accel, model, cam)
     util.assert_bit_equal(got, O.render(L.KERNEL_BASIC_CU, sb, util.default_camera(), 128, 96))
     r.close(); accel.close(); model.close(); cam.close()
+
+
+def test_plugin_device_api_lt_trace():
+    """A plug-in that includes lens_trace_b200_device.cuh and calls lt_trace(): same hit ids and t as the built-in
+    kernels (bit for bit), any-hit shadow query works."""
+    from lens_trace_b200 import capi
+    ctx = capi.Context(0)
+    for name in ("cornell_box", "cornell_box_lens"):
+        sb = util.scene(name)
+        sc = ctx.upload(sb)
+        pid = ctx.plugin_load(os.path.join(util.ROOT, "tests", "plugins", "fast_trace.cu"))
+        for yaw in (0.0, 0.04):
+            cam = util.default_camera(yaw)
+            got = ctx.render_plugin(sc, cam, pid, 240, 160, block=(8, 8))
+            ids, hit, tuv = ctx.primary_hits(sc, cam, L.KERNEL_BASIC_CU, 240, 160)
+            m = hit == 1
+            np.testing.assert_array_equal(got[..., 0].view(np.int32)[m] - 1, ids[m])
+            assert (got[..., 0][~m] == 0).all()
+            util.assert_bit_equal(got[..., 1][m], tuv[..., 0][m], "t from lt_trace vs built-in kernel")
+            assert set(np.unique(got[..., 2]).tolist()) <= {0.0, 1.0} and got[..., 2][m].max() == 1.0
+        sc.release()
+    ctx.close()
