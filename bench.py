@@ -250,6 +250,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: every GPU renders the workload's frames (N x the samples); strong: the workload's "
+                         "frames are divided among the GPUs (BASELINE configs[4]: 256 spp split over 1/2/4/8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true")
     ap.add_argument("--no-cull", action="store_true", help="skip the secondary opt-in culled measurement")
@@ -280,6 +283,10 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     model, kernel, w, h, frames, depth, desc = WORKLOADS[args.workload]
+    if args.scaling == "strong":
+        if frames % world:
+            sys.exit("bench.py: --scaling strong needs the workload's %d frames to divide by %d GPUs" % (frames, world))
+        frames //= world  # this rank's share; frame k of rank r has frameCount r + k*world, weight 1/(frames*world)
     sb = load_scene(model)
     ctx = capi.Context(local_rank)
     scene = ctx.upload(sb)
@@ -439,7 +446,7 @@ def main():
                                   "frac": alg_bytes / k_s / 1e9 / pk["hbm_gbs"], "peak_source": pk["source"]}})
         line = {
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "description": desc, "width": w, "height": h,
                        "frames_per_step_per_gpu": frames, "max_ray_depth": depth, "rays_per_step": rays,

@@ -356,3 +356,24 @@ def test_gpu_lbvh_builder_large(ctx, tmp_path):
     np.testing.assert_allclose(a[2][..., 0][hit == 1], tuv[..., 0][hit == 1], rtol=1e-5)
     msc.release()
     sc.release()
+
+
+def test_depth_four_and_frame_stride(ctx):
+    """imageDimensions[2] = 4 (three floats written per pixel, stride 4, basic.cu:344,361-363) and a frame stride
+    (the frames one rank of a sample split renders) against the oracle."""
+    sb, sc = gpu_scene(ctx, "cornell_box")
+    w, h = 72, 40
+    cam = util.default_camera(0.0, 1)
+    got = ctx.render(sc, cam, capi.make_params(L.KERNEL_BASIC_CU, w, h, depth=4))
+    want = O.render(L.KERNEL_BASIC_CU, sb, cam, w, h, depth=4)
+    util.assert_bit_equal(got[..., :3], want[..., :3])
+    for pipe in PIPES:
+        ctx.accum_reset()
+        p = capi.make_params(L.KERNEL_GI, w, h, max_ray_depth=3, frames=3, frame_stride=4,
+                             accum_mode=L.ACCUM_WEIGHTED_SUM, accum_weight=0.25, flags=pipe)
+        got = ctx.render(sc, util.default_camera(0.0, 2), p)  # frameCount 2, 6, 10
+        acc = np.zeros((h, w, 3), np.float32)
+        for fc in (2, 6, 10):
+            s = O.render(L.KERNEL_GI, sb, util.default_camera(0.0, fc), w, h, max_ray_depth=3, threads=0)
+            acc = (acc + np.float32(0.25) * s).astype(np.float32)
+        assert_images_match(got, acc, "weighted sum with stride", max_outliers=3)
