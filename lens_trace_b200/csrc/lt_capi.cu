@@ -610,11 +610,10 @@ static int primary_hits_impl(lt_ctx* ctx, lt_scene* scene, const void* camera28,
     return fail(ctx, LT_ERR_INVALID, "lt_primary_hits: bad argument");
   CK(cudaSetDevice(ctx->device));
   size_t n = (size_t)width * height;
-  int *dIds = nullptr, *dHit = nullptr;
-  float* dTuv = nullptr;
-  CK(cudaMalloc(&dIds, n * sizeof(int)));
-  CK(cudaMalloc(&dHit, n * sizeof(int)));
-  CK(cudaMalloc(&dTuv, 3 * n * sizeof(float)));
+  int* dAll = nullptr;  // one allocation: ids | hit | t,u,v
+  CK(cudaMalloc(&dAll, 5 * n * sizeof(int)));
+  int *dIds = dAll, *dHit = dAll + n;
+  float* dTuv = reinterpret_cast<float*>(dAll + 2 * n);
   RefCamera cam;
   memcpy(&cam, camera28, sizeof(cam));
   lt_launch_primary_hits(scene->dev, cam, kernel, flags, width, height, dIds, dHit, dTuv, ctx->stream);
@@ -623,9 +622,7 @@ static int primary_hits_impl(lt_ctx* ctx, lt_scene* scene, const void* camera28,
   if (e == cudaSuccess && ids) e = cudaMemcpy(ids, dIds, n * sizeof(int), cudaMemcpyDeviceToHost);
   if (e == cudaSuccess && hit) e = cudaMemcpy(hit, dHit, n * sizeof(int), cudaMemcpyDeviceToHost);
   if (e == cudaSuccess && tuv) e = cudaMemcpy(tuv, dTuv, 3 * n * sizeof(float), cudaMemcpyDeviceToHost);
-  cudaFree(dIds);
-  cudaFree(dHit);
-  cudaFree(dTuv);
+  cudaFree(dAll);
   if (e != cudaSuccess) return fail(ctx, LT_ERR_CUDA, std::string("lt_primary_hits: ") + cudaGetErrorString(e));
   return LT_OK;
 }
