@@ -736,12 +736,11 @@ __device__ __forceinline__ float make_shadow_ray(const LtSceneDev& sc, const flo
 __device__ __forceinline__ void sample_hemisphere(float u1, float u2, const float up[3], float dir[4]) {
   float z = u1;
   float r = FSQRT(fmaxf(0.0f, FSUB(1.0f, FMUL(z, z))));
-  double phi = __dmul_rn(6.28318530717958647692, (double)u2);
-  double sp, cp;
-  sincos(phi, &sp, &cp);
-  float hx = (float)__dmul_rn((double)r, cp);
+  // `float phi = 2.0 * M_PI * uv.y;` (:72): the product is fp64, phi and its cos/sin are FP32
+  float phi = (float)__dmul_rn(6.28318530717958647692, (double)u2);
+  float hx = FMUL(r, cosf(phi));
   float hy = z;
-  float hz = (float)__dmul_rn((double)r, sp);
+  float hz = FMUL(r, sinf(phi));
   const float cx = 0.0072f, cy = 1.0f, cz = 0.0034f;
   float rx = FSUB(FMUL(up[1], cz), FMUL(up[2], cy));
   float ry = FSUB(FMUL(up[2], cx), FMUL(up[0], cz));
@@ -848,7 +847,8 @@ __device__ __forceinline__ bool shade_step(const LtSceneDev& sc, const PathConst
   } else {
     // the shadow ray's direction is positionToLight, its origin the shaded position
     bool lit = (h.hit == 0);
-    float d = FADD(FADD(FMUL(r.dx, ps.nrm[0]), FMUL(r.dy, ps.nrm[1])), FMUL(r.dz, ps.nrm[2]));
+    // float4 dot: the w term is 0 * normal.w = +0, which turns a -0 sum into +0
+    float d = FADD(FADD(FADD(FMUL(r.dx, ps.nrm[0]), FMUL(r.dy, ps.nrm[1])), FMUL(r.dz, ps.nrm[2])), 0.0f);
     if (ps.stage == ST_SHADOW_DIRECT) {  // basic_lighting.cl:272-274, global_illumination.cl:296-309
       if (lit) {
         ps.direct[0] = FMUL(ps.diffuse[0], d); ps.direct[1] = FMUL(ps.diffuse[1], d); ps.direct[2] = FMUL(ps.diffuse[2], d);
@@ -918,7 +918,7 @@ __device__ __forceinline__ void sample_colour(const PathConsts& pc, const PathSt
 }
 
 // basic_lighting.cl:309-320 / global_illumination.cl:408-419: first sample copies, later samples
-// blend with a = (25 - x)/25; the linear kernel clamps the finished frame to [0,1]
+// blend with a = (25 - x)/25
 __device__ __forceinline__ void blend_sample(const PathConsts& pc, int sample, const float c[3], float frameColor[3]) {
   if (pc.samplesPerFrame == 1 || sample == 0) {
     frameColor[0] = c[0]; frameColor[1] = c[1]; frameColor[2] = c[2];
@@ -930,7 +930,9 @@ __device__ __forceinline__ void blend_sample(const PathConsts& pc, int sample, c
   }
 }
 __device__ __forceinline__ void finish_frame_colour(const PathConsts& pc, int kernelMode, float frameColor[3]) {
-  if (pc.samplesPerFrame == 25 && kernelMode == 0) {
+  // every stochastic kernel file clamps in linearKernel and not in tileKernel (basic_lighting.cl:318-320
+  // vs :365-367, accumulator.cl:316-318 vs :356-358, both global_illumination.cl)
+  if (kernelMode == 0) {
 #pragma unroll
     for (int k = 0; k < 3; k++) frameColor[k] = fminf(fmaxf(frameColor[k], 0.0f), 1.0f);
   }

@@ -44,6 +44,8 @@ def load():
         lib.lto_random.restype = C.c_float
         lib.lto_hemisphere.argtypes = [C.c_float, C.c_float, C.c_void_p, C.c_void_p]
         lib.lto_hemisphere.restype = None
+        lib.lto_set_fp_mode.argtypes = [C.c_int]
+        lib.lto_set_fp_mode.restype = None
         lib.lto_cuda_cosf.argtypes = [C.c_float]
         lib.lto_cuda_cosf.restype = C.c_float
         lib.lto_cuda_sinf.argtypes = [C.c_float]
@@ -107,3 +109,21 @@ def hemisphere(u1, u2, up):
     out = np.zeros(4, np.float32)
     lib.lto_hemisphere(float(u1), float(u2), upa.ctypes.data, out.ctypes.data)
     return out
+
+
+FP_DEVICE, FP_PLAIN = 0, 1
+
+
+class fp_mode:
+    """`with fp_mode(FP_PLAIN): ...` -- evaluate the restatement as plain C (see lt_oracle.h) inside the block."""
+
+    def __init__(self, mode):
+        self.mode = mode
+
+    def __enter__(self):
+        lib = load()
+        self.prev = lib.lto_get_fp_mode()
+        lib.lto_set_fp_mode(self.mode)
+
+    def __exit__(self, *exc):
+        load().lto_set_fp_mode(self.prev)
