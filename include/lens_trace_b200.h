@@ -64,8 +64,11 @@ enum lt_flags {
                              (+1e-4 relative margin).  Does less work than the reference's traversal; output is
                              identical on every tested scene but that is validated, not guaranteed. */
   LT_FLAG_MEGAKERNEL = 1 << 2, /* stochastic kernels: force the one-thread-per-pixel persistent kernel */
-  LT_FLAG_WAVEFRONT = 1 << 3   /* stochastic kernels: force the wavefront pipeline (default: chosen by size;
+  LT_FLAG_WAVEFRONT = 1 << 3,  /* stochastic kernels: force the wavefront pipeline (default: chosen by size;
                                   both produce bit-identical output) */
+  LT_FLAG_NO_THREADED = 1 << 4 /* small scenes: traverse with the stack kernels instead of the stackless threaded
+                                  tree (default for scenes whose 8 octant copies stay cache resident; identical
+                                  output, kept selectable so tests can compare the two) */
 };
 
 typedef struct lt_ctx lt_ctx;

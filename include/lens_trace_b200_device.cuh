@@ -79,6 +79,21 @@ struct __align__(16) LtTri {
 };
 static_assert(sizeof(LtTri) == 48, "triangle record is 48 bytes");
 
+// Threaded ("skip pointer") form of the same tree, built for scenes small enough that eight copies stay
+// cache resident.  The reference visits children near-first by the sign of the ray direction on the split
+// axis and never culls by t, so for each of the 8 sign octants the visit order of the whole tree is one
+// fixed depth-first sequence.  Copy o (records [o*nodeCount, (o+1)*nodeCount)) holds the reference nodes in
+// that sequence: the next record is the first node to visit after a box hit, `skip` the first node after
+// the subtree -- a traversal is `i = hit && inner ? i + 1 : skip` with no stack.  The bounds are stored
+// already selected by the octant's dirIsNeg (basic.cu:88-91), so the slab test needs no selects either.
+// One 32-byte sector, two 128-bit loads.
+struct __align__(16) LtThreadNode {
+  float4 a;  // lo.x lo.y lo.z hi.x      lo = dirIsNeg ? boundsMax : boundsMin, hi the other one
+  float4 b;  // hi.y hi.z bits(link) bits(skip)   link < 0: leaf, ~primitivesOffset; >= 0: inner node
+             //                                   skip: absolute record index, LT_DONE at the end of the tree
+};
+static_assert(sizeof(LtThreadNode) == 32, "threaded node is 32 bytes");
+
 #define LT_DONE ((int)0x80000000)  // traversal sentinel (== ~0x7fffffff, never a primitive)
 
 struct LtSceneDev {
@@ -93,6 +108,7 @@ struct LtSceneDev {
   int rootCount;              // primitiveCount of a leaf root (stats only)
   int stackDepth;             // entries a traversal stack needs (tree depth), <= 64
   int nodeCount, primCount, matCount;
+  const LtThreadNode* tnodes;  // 8 * nodeCount threaded records, or NULL (scene too large for the copies)
 };
 
 

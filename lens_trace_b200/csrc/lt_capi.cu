@@ -36,6 +36,7 @@ struct lt_scene {
   RefLights* dLights = nullptr;
   LtWideNode* dWide = nullptr;
   LtTri* dTris = nullptr;
+  LtThreadNode* dThread = nullptr;  // 8 octant copies in visit order, small scenes only
   LtSceneDev dev = {};
 };
 
@@ -160,7 +161,60 @@ extern "C" void lt_scene_release(lt_ctx* ctx, lt_scene* s) {
   cudaFree(s->dLights);
   cudaFree(s->dWide);
   cudaFree(s->dTris);
+  cudaFree(s->dThread);
   delete s;
+}
+
+// Threaded form of the tree (LtThreadNode, lens_trace_b200_device.cuh): eight copies of the node array, copy o in
+// the order the reference's traversal visits the nodes for rays of sign octant o.  Built on the host: it is
+// only made for trees of at most lt_threaded_max_nodes() nodes (8 x 32 B x N must stay cache resident).
+static int lt_threaded_max_nodes() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("LT_THREADED_MAX_NODES");
+    v = e ? atoi(e) : 65536;  // 16 MB of records at the limit
+    if (v < 0) v = 0;
+  }
+  return v;
+}
+
+static void build_threaded(const RefNode* nodes, int n, std::vector<LtThreadNode>& out) {
+  out.resize((size_t)8 * n);
+  std::vector<int> size(n), stack;
+  for (int i = n - 1; i >= 0; i--)  // children follow their parent in the depth-first array
+    size[i] = nodes[i].primitiveCount > 0 ? 1 : 1 + size[i + 1] + size[nodes[i].offset];
+  auto bitsf = [](int v) { float f; memcpy(&f, &v, 4); return f; };
+  for (int o = 0; o < 8; o++) {
+    const int base = o * n;
+    int pos = 0;
+    stack.clear();
+    stack.push_back(0);
+    while (!stack.empty()) {
+      int i = stack.back();
+      stack.pop_back();
+      const RefNode& r = nodes[i];
+      const bool leaf = r.primitiveCount > 0;
+      const float* lo[3];
+      const float* hi[3];
+      for (int k = 0; k < 3; k++) {
+        bool neg = (o >> k) & 1;
+        lo[k] = neg ? r.boundsMax : r.boundsMin;
+        hi[k] = neg ? r.boundsMin : r.boundsMax;
+      }
+      int end = pos + size[i];
+      int skip = end >= n ? LT_DONE : base + end;
+      LtThreadNode& t = out[(size_t)base + pos];
+      t.a = make_float4(lo[0][0], lo[1][1], lo[2][2], hi[0][0]);
+      t.b = make_float4(hi[1][1], hi[2][2], bitsf(leaf ? ~r.offset : 0), bitsf(skip));
+      pos++;
+      if (!leaf) {
+        bool neg = (o >> r.axis) & 1;  // basic.cu:180-186: second child first when the direction is negative
+        int nearC = neg ? r.offset : i + 1, farC = neg ? i + 1 : r.offset;
+        stack.push_back(farC);
+        stack.push_back(nearC);
+      }
+    }
+  }
 }
 
 // Re-flatten on the device (inner-node ranks -> 64-byte child-pair nodes, 48-byte triangles) and fill the
@@ -186,6 +240,18 @@ static int finish_scene(lt_ctx* ctx, lt_scene* s, int nNodes, int nPrims, int nM
     lt_launch_exclusive_scan(dTemp, tempBytes, dFlags, dRank, nNodes, st);
     lt_launch_reflatten(s->dNodes, nNodes, s->dPrims, nPrims, dRank, s->dWide, s->dTris, st);
     A(cudaGetLastError());
+  }
+  if (e == cudaSuccess && nNodes <= lt_threaded_max_nodes()) {
+    std::vector<RefNode> hNodes((size_t)nNodes);
+    std::vector<LtThreadNode> hThread;
+    A(cudaMemcpyAsync(hNodes.data(), s->dNodes, sizeof(RefNode) * (size_t)nNodes, cudaMemcpyDeviceToHost, st));
+    A(cudaStreamSynchronize(st));
+    if (e == cudaSuccess) {
+      build_threaded(hNodes.data(), nNodes, hThread);
+      A(cudaMalloc(&s->dThread, sizeof(LtThreadNode) * hThread.size()));
+      A(cudaMemcpyAsync(s->dThread, hThread.data(), sizeof(LtThreadNode) * hThread.size(), cudaMemcpyHostToDevice, st));
+      A(cudaStreamSynchronize(st));  // hThread is pageable and goes out of scope
+    }
   }
   A(cudaEventRecord(ctx->ev1, st));
   A(cudaStreamSynchronize(st));
@@ -213,6 +279,7 @@ static int finish_scene(lt_ctx* ctx, lt_scene* s, int nNodes, int nPrims, int nM
   d.nodeCount = nNodes;
   d.primCount = nPrims;
   d.matCount = nMats;
+  d.tnodes = s->dThread;
   return LT_OK;
 }
 

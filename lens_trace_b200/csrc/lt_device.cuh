@@ -165,12 +165,33 @@ __device__ __forceinline__ int trav_pop(Trav& t, const int* __restrict__ stk) {
   return can ? v : LT_DONE;
 }
 
+// ---- shared-memory access through 32-bit shared addresses, 256-bit node loads ----
+__device__ __forceinline__ void sts32(unsigned addr, int v) {
+  asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ int lds32(unsigned addr) {
+  int v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+#define LT_SMEM_STRIDE_LOG2 9  // LT_BLOCK * sizeof(int) = 512 bytes between levels of one thread
+
+// One 256-bit read-only load (LDG.E.ENL2.256.CONSTANT, sm_100): a 32-byte record costs one L1 request -- and, for
+// the divergent addresses of a traversal, one wavefront per distinct 128-byte line -- instead of two.
+__device__ __forceinline__ void ldg256(const void* p, float4& a, float4& b) {
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+               : "l"(p));
+}
+
 // one inner-node step; requires t.cur >= 0
 template <bool STATS>
 __device__ __forceinline__ void trav_node_step(Trav& t, const LtSceneDev& sc, int* __restrict__ stk, LtCounters& cnt) {
   const float4* np = reinterpret_cast<const float4*>(sc.wnodes + t.cur);
-  float4 bx = __ldg(np), by = __ldg(np + 1), bz = __ldg(np + 2);
-  int4 m = __ldg(reinterpret_cast<const int4*>(np) + 3);
+  float4 bx, by, bz, mf;
+  ldg256(np, bx, by);
+  ldg256(np + 2, bz, mf);
+  int4 m = make_int4(__float_as_int(mf.x), __float_as_int(mf.y), __float_as_int(mf.z), __float_as_int(mf.w));
   bool hl, hr;
   // The select-chain test is valid for every ray, the interval test only for rays without
   // non-finite reciprocals; both give the same answer where both apply.  If any lane that is at this
@@ -305,24 +326,17 @@ __device__ __forceinline__ bool trav_iter(Trav& t, const LtSceneDev& sc, int* __
 // addresses (no generic-pointer conversion per access), the two children of a node are classified once
 // and a hit leaf child is recorded in the FIFO inside the node step itself (no pop/drain round trip);
 // only a leaf that had to wait on the stack behind an inner sibling is recorded after being popped.
-__device__ __forceinline__ void sts32(unsigned addr, int v) {
-  asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
-}
-__device__ __forceinline__ int lds32(unsigned addr) {
-  int v;
-  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
-  return v;
-}
-#define LT_SMEM_STRIDE_LOG2 9  // LT_BLOCK * sizeof(int) = 512 bytes between levels of one thread
-
 template <bool STATS>
 __device__ __forceinline__ bool trav_iter_lean(Trav& t, const LtSceneDev& sc, unsigned stkAddr, unsigned fifoAddr,
                                                float epsThr, int nodeSteps, int triTests, LtCounters& cnt) {
-  for (int steps = 0; steps < nodeSteps && t.cur != LT_DONE && t.qTail - t.qHead <= LT_MAX_BATCH - 2; steps++) {
+  // one step records up to three leaves (near child, far child, and a leaf popped behind them)
+  for (int steps = 0; steps < nodeSteps && t.cur != LT_DONE && t.qTail - t.qHead <= LT_MAX_BATCH - 3; steps++) {
     if (t.cur >= 0) {
       const float4* np = reinterpret_cast<const float4*>(sc.wnodes + t.cur);
-      float4 bx = __ldg(np), by = __ldg(np + 1), bz = __ldg(np + 2);
-      int4 m = __ldg(reinterpret_cast<const int4*>(np) + 3);
+      float4 bx, by, bz, mf;
+      ldg256(np, bx, by);
+      ldg256(np + 2, bz, mf);
+      int4 m = make_int4(__float_as_int(mf.x), __float_as_int(mf.y), __float_as_int(mf.z), __float_as_int(mf.w));
       unsigned hits;  // bit 0: left child box hit, bit 1: right child box hit
       if (__any_sync(__activemask(), (t.negMask & LT_EXACT_SLAB) != 0u)) {
         bool nx = t.negMask & 1u, ny = t.negMask & 2u, nz = t.negMask & 4u;
@@ -387,6 +401,84 @@ __device__ __forceinline__ bool trav_iter_lean(Trav& t, const LtSceneDev& sc, un
     t.qHead++;
     if (STATS) cnt.triTests++;
     if (tri_test(sc.tris, prim, t.r, epsThr, t.h)) {
+      t.h.prim = prim;
+      t.h.hit = 1;
+      if (t.anyHit) {
+        t.cur = LT_DONE;
+        t.qHead = t.qTail;
+      }
+    }
+  }
+  return t.cur == LT_DONE && t.qHead == t.qTail;
+}
+
+// ---- stackless traversal of the threaded tree (LtThreadNode, small scenes) -----------------------
+// Same box tests and triangle tests in the same order as the stack traversal above, hence the same hits:
+// the records of the ray's sign octant are laid out in visit order, so a step is one box test and
+// `cur = hit && inner ? cur + 1 : skip`.  No stack, no near/far selection, no per-axis min/max: the
+// record's bounds are already the dirIsNeg-selected ones, so for rays with finite reciprocals
+// (lo - o) * inv <= (hi - o) * inv per axis and the select chain of basic.cu:136-154 reduces to
+// max3(entries) <= min3(exits) && min3(exits) > 0 on the same FSUB/FMUL products.
+__device__ __forceinline__ void trav_begin_threaded(Trav& t, const LtSceneDev& sc, int ignore, float tInit, bool anyHit) {
+  t.ix = FRCP(t.r.dx);
+  t.iy = FRCP(t.r.dy);
+  t.iz = FRCP(t.r.dz);
+  t.negMask = (t.ix < 0.0f ? 1u : 0u) | (t.iy < 0.0f ? 2u : 0u) | (t.iz < 0.0f ? 4u : 0u);
+  t.cur = (int)(t.negMask & 7u) * sc.nodeCount;  // the root record of the ray's octant copy
+  if (!(finite3(t.ix, t.iy, t.iz) && finite3(t.r.ox, t.r.oy, t.r.oz))) t.negMask |= LT_EXACT_SLAB;
+  t.h.t = tInit; t.h.u = 0.0f; t.h.v = 0.0f; t.h.prim = 0; t.h.hit = 0;
+  t.ignore = ignore;
+  t.anyHit = anyHit;
+  t.sp = 0;
+  t.qHead = t.qTail = 0;
+}
+
+// node phase, EXACT = select chain (valid for every ray) or interval form (rays with finite reciprocals).
+// Each step records at most one leaf, so `maxSteps` <= free FIFO slots needs no per-step capacity check.
+template <bool EXACT>
+__device__ __forceinline__ void trav_threaded_nodes(Trav& t, const LtThreadNode* __restrict__ tn, unsigned fifoAddr,
+                                                    int maxSteps, int notIgnore) {
+  for (int steps = 0; steps < maxSteps && t.cur != LT_DONE; steps++) {
+    float4 a, b;
+    ldg256(tn + t.cur, a, b);
+    float tx0 = FMUL(FSUB(a.x, t.r.ox), t.ix), tx1 = FMUL(FSUB(a.w, t.r.ox), t.ix);
+    float ty0 = FMUL(FSUB(a.y, t.r.oy), t.iy), ty1 = FMUL(FSUB(b.x, t.r.oy), t.iy);
+    float tz0 = FMUL(FSUB(a.z, t.r.oz), t.iz), tz1 = FMUL(FSUB(b.y, t.r.oz), t.iz);
+    bool hit;
+    if (EXACT) {
+      bool miss1 = (tx0 > ty1) || (ty0 > tx1);
+      float lo = (ty0 > tx0) ? ty0 : tx0;
+      float hi = (ty1 < tx1) ? ty1 : tx1;
+      bool miss2 = (lo > tz1) || (tz0 > hi);
+      float hi2 = (tz1 < hi) ? tz1 : hi;
+      hit = !miss1 && !miss2 && (hi2 > 0.0f);
+    } else {
+      float lo = fmaxf(fmaxf(tx0, ty0), tz0);
+      float hi = fminf(fminf(tx1, ty1), tz1);
+      hit = lo <= hi && hi > 0.0f;
+    }
+    int link = __float_as_int(b.z), skip = __float_as_int(b.w);
+    if (hit && link < 0 && link != notIgnore) {
+      sts32(fifoAddr + ((unsigned)(t.qTail & (LT_MAX_BATCH - 1)) << LT_SMEM_STRIDE_LOG2), ~link);
+      t.qTail++;
+    }
+    t.cur = (hit && link >= 0) ? t.cur + 1 : skip;
+  }
+}
+
+__device__ __forceinline__ bool trav_iter_threaded(Trav& t, const LtThreadNode* __restrict__ tn,
+                                                   const LtTri* __restrict__ tris, unsigned fifoAddr, float epsThr,
+                                                   int nodeSteps, int triTests) {
+  // rays change only between iterations, so which slab form the warp runs is decided once per iteration
+  const bool exact = __any_sync(__activemask(), (t.negMask & LT_EXACT_SLAB) != 0u);
+  const int maxSteps = min(nodeSteps, LT_MAX_BATCH - (t.qTail - t.qHead));
+  const int notIgnore = ~t.ignore;  // a leaf's link is ~primitivesOffset
+  if (exact) trav_threaded_nodes<true>(t, tn, fifoAddr, maxSteps, notIgnore);
+  else trav_threaded_nodes<false>(t, tn, fifoAddr, maxSteps, notIgnore);
+  for (int k = 0; k < triTests && t.qHead != t.qTail; k++) {
+    int prim = lds32(fifoAddr + ((unsigned)(t.qHead & (LT_MAX_BATCH - 1)) << LT_SMEM_STRIDE_LOG2));
+    t.qHead++;
+    if (tri_test(tris, prim, t.r, epsThr, t.h)) {
       t.h.prim = prim;
       t.h.hit = 1;
       if (t.anyHit) {
@@ -509,6 +601,13 @@ __host__ inline size_t lt_traversal_smem(const LtSceneDev& sc, bool cull) {
 template <bool STATS>
 __device__ __forceinline__ void trace(Trav& t, const LtSceneDev& sc, int ignore, float tInit, float epsThr,
                                       bool anyHit, int* __restrict__ stk, int* __restrict__ list, LtCounters& cnt) {
+  if (!STATS && sc.tnodes != nullptr) {  // small scene: stackless traversal of the threaded tree, same tests
+    trav_begin_threaded(t, sc, ignore, tInit, anyHit);
+    const unsigned fifoAddr = (unsigned)__cvta_generic_to_shared(list);
+    while (!trav_iter_threaded(t, sc.tnodes, sc.tris, fifoAddr, epsThr, LT_MAX_BATCH, LT_MAX_BATCH)) {
+    }
+    return;
+  }
   trav_begin<STATS>(t, sc, ignore, tInit, anyHit, cnt);
   while (t.cur != LT_DONE) {
     int n = trav_collect<STATS>(t, sc, stk, list, LT_MAX_BATCH, cnt);

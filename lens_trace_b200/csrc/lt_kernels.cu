@@ -105,11 +105,13 @@ __global__ void __launch_bounds__(LT_BLOCK) k_path(LtSceneDev sc, LtLaunch L, fl
   ps.depth = 0;
   path_reset(ps);
 
+  const bool threaded = !STATS && sc.tnodes != nullptr;  // small scene: stackless threaded tree, same tests
   Trav t;
   t.r = cameraRay;
   bool traversing = false;
   if (alive) {
-    trav_begin<STATS>(t, sc, -1, pc.tInit, false, cnt);
+    if (threaded) trav_begin_threaded(t, sc, -1, pc.tInit, false);
+    else trav_begin<STATS>(t, sc, -1, pc.tInit, false, cnt);
     traversing = (t.cur != LT_DONE);
   }
 
@@ -144,7 +146,8 @@ __global__ void __launch_bounds__(LT_BLOCK) k_path(LtSceneDev sc, LtLaunch L, fl
         tStart = pc.tInit;
         anyHit = false;
       }
-      trav_begin<STATS>(t, sc, ignore, tStart, anyHit, cnt);
+      if (threaded) trav_begin_threaded(t, sc, ignore, tStart, anyHit);
+      else trav_begin<STATS>(t, sc, ignore, tStart, anyHit, cnt);
       traversing = (t.cur != LT_DONE);
     }
     if (!__any_sync(0xffffffffu, alive)) break;
@@ -156,7 +159,9 @@ __global__ void __launch_bounds__(LT_BLOCK) k_path(LtSceneDev sc, LtLaunch L, fl
       bool waiting = __any_sync(0xffffffffu, alive && !traversing);
       if (waiting && __popc(active) < L.refillThreshold) break;
       if (traversing) {
-        if (L.batchClosest > 0) {  // leaf-list form: whole batches of box tests, then the recorded triangles
+        if (threaded) {
+          traversing = !trav_iter_threaded(t, sc.tnodes, sc.tris, fifoAddr, pc.epsThr, 2 * L.iterNodeSteps, L.iterTriTests);
+        } else if (L.batchClosest > 0) {  // leaf-list form: whole batches of box tests, then the recorded triangles
           int n = trav_collect<STATS>(t, sc, stk, list, t.anyHit ? L.batchAnyHit : L.batchClosest, cnt);
           trav_test<STATS>(t, sc, list, n, pc.epsThr, cnt);
           traversing = (t.cur != LT_DONE);
@@ -291,8 +296,17 @@ static size_t stack_bytes(const LtSceneDev& sc, bool cull) { return lt_traversal
 
 static int tile_blocks(int width, int height) { return ((width + 15) / 16) * ((height + 7) / 8); }
 
-int lt_launch_render(const LtSceneDev& sc, const LtLaunch& L, float* dOut, LtCounters* dCounters,
+// the threaded tree is used by the exact, uncounted kernels only (the stats kernels count in the stack traversal,
+// whose tests are the same ones; LT_FLAG_NO_THREADED = 16 selects the stack traversal for comparison)
+static LtSceneDev scene_for_flags(const LtSceneDev& sc, int flags) {
+  LtSceneDev s = sc;
+  if (flags & (1 | 2 | 16)) s.tnodes = nullptr;
+  return s;
+}
+
+int lt_launch_render(const LtSceneDev& scIn, const LtLaunch& L, float* dOut, LtCounters* dCounters,
                      cudaStream_t stream) {
+  const LtSceneDev sc = scene_for_flags(scIn, L.flags);
   int blocks = tile_blocks(L.width, L.height);
   size_t smem = stack_bytes(sc, (L.flags & 2) != 0);
   bool stats = (L.flags & 1) != 0;
@@ -307,8 +321,9 @@ int lt_launch_render(const LtSceneDev& sc, const LtLaunch& L, float* dOut, LtCou
   return 1;
 }
 
-int lt_launch_primary_hits(const LtSceneDev& sc, const RefCamera& cam, int kernel, int flags, int width, int height,
+int lt_launch_primary_hits(const LtSceneDev& scIn, const RefCamera& cam, int kernel, int flags, int width, int height,
                            int* dIds, int* dHit, float* dTuv, cudaStream_t stream) {
+  const LtSceneDev sc = scene_for_flags(scIn, flags);
   k_primary_hits<<<tile_blocks(width, height), LT_BLOCK, stack_bytes(sc, (flags & 2) != 0), stream>>>(
       sc, cam, kernel, flags, width, height, dIds, dHit, dTuv);
   return 1;

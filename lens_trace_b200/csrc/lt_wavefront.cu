@@ -148,11 +148,16 @@ __global__ void k_wf_reset(LtWfBuffers B) {
 }
 
 // persistent trace: lanes pull queue entries through one warp-aggregated atomic per refill
-template <bool STATS>
+// THREADED: stackless traversal of the per-octant threaded tree (sc.tnodes, small scenes); shared memory then
+// holds only the leaf FIFO.  Same tests in the same order, hence the same hit records.
+template <bool STATS, bool THREADED>
 __global__ void __launch_bounds__(WF_BLOCK) k_wf_trace(LtSceneDev sc, LtLaunch L, LtWfBuffers B, int q,
                                                        LtCounters* gcnt) {
-  LT_SMEM_POINTERS(sc)
-  const bool cull = (L.flags & 2) != 0;  // LT_FLAG_CULL: closest-hit rays skip subtrees behind the current hit
+  extern __shared__ int smemStack[];
+  int* stk = smemStack + threadIdx.x;
+  int* list = smemStack + (THREADED ? 0 : lt_stack_levels(sc) * LT_BLOCK) + threadIdx.x;
+  float* tstk = reinterpret_cast<float*>(smemStack + (lt_stack_levels(sc) + LT_MAX_BATCH) * LT_BLOCK) + threadIdx.x;
+  const bool cull = !THREADED && (L.flags & 2) != 0;  // LT_FLAG_CULL: closest-hit rays skip subtrees behind the current hit
   const int nFront = B.counts[q];
   const int n = nFront + B.counts[3 + q];  // virtual entries: front region, then the back region
   const float epsThr = lt_eps(L.kernel);
@@ -190,7 +195,8 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_trace(LtSceneDev sc, LtLaunch L
           t.r.ox = o.x; t.r.oy = o.y; t.r.oz = o.z;
           t.r.dx = d.x; t.r.dy = d.y; t.r.dz = d.z;
           unsigned bits = (unsigned)__float_as_int(d.w);
-          trav_begin<STATS>(t, sc, (int)(bits & 0x7fffffffu) - 1, o.w, (bits >> 31) != 0u, cnt);
+          if (THREADED) trav_begin_threaded(t, sc, (int)(bits & 0x7fffffffu) - 1, o.w, (bits >> 31) != 0u);
+          else trav_begin<STATS>(t, sc, (int)(bits & 0x7fffffffu) - 1, o.w, (bits >> 31) != 0u, cnt);
           entry = idx;
           if (t.cur == LT_DONE) {  // missed the root box: finished already
             B.hits[idx] = make_float4(t.h.t, 0.0f, 0.0f, __int_as_float(0));
@@ -206,7 +212,9 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_trace(LtSceneDev sc, LtLaunch L
     }
     if (has) {
       bool finished;
-      if (cull && !t.anyHit) {  // a round holds one kind of ray, so this does not split warps
+      if (THREADED) {
+        finished = trav_iter_threaded(t, sc.tnodes, sc.tris, fifoAddr, epsThr, L.iterNodeSteps, L.iterTriTests);
+      } else if (cull && !t.anyHit) {  // a round holds one kind of ray, so this does not split warps
         for (int k = 0; k < 2 * L.iterNodeSteps && t.cur != LT_DONE; k++)
           trav_step_cull<STATS>(t, sc, stk, tstk, epsThr, cnt);
         finished = t.cur == LT_DONE;
@@ -318,6 +326,13 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_accumulate(LtLaunch L, LtWfBuff
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+#include <stdlib.h>
+static int lt_env_int(const char* name, int dflt) {  // tuning knobs for experiments; defaults are the measured choice
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+#define LT_LAUNCH_FLAG_NO_THREADED 16  // == LT_FLAG_NO_THREADED (include/lens_trace_b200.h)
+
 size_t lt_wf_bytes_per_path() {
   return sizeof(float4) * (4 + 1 + 2 * 2 + 1) + sizeof(int) * 2;  // state, frame colour, 2 queues, hits, path ids
 }
@@ -351,9 +366,11 @@ size_t lt_wf_workspace_bytes_padded(long long nPaths) {
   return lt_wf_workspace_bytes(nPaths) + 256 * 16;
 }
 
-int lt_launch_render_wavefront(const LtSceneDev& sc, const LtLaunch& L, float* dOut, LtCounters* dCounters,
+int lt_launch_render_wavefront(const LtSceneDev& scIn, const LtLaunch& L, float* dOut, LtCounters* dCounters,
                                void* workspace, int batchFrames, int smCount, cudaStream_t stream,
                                cudaEvent_t* traceEvents, int maxTraceLaunches, int* traceLaunches) {
+  LtSceneDev sc = scIn;
+  if (L.flags & (1 | 2 | LT_LAUNCH_FLAG_NO_THREADED)) sc.tnodes = nullptr;  // stats / culled / forced stack traversal
   int pairs = 0;
   auto mark = [&](int which) {  // which: 0 = before, 1 = after a traversal launch
     if (traceEvents && pairs < maxTraceLaunches) cudaEventRecord(traceEvents[2 * pairs + which], stream);
@@ -369,6 +386,16 @@ int lt_launch_render_wavefront(const LtSceneDev& sc, const LtLaunch& L, float* d
   int blocksPerSm = (int)((200 * 1024) / smem);  // shared memory is what limits residency of the persistent kernel
   if (blocksPerSm > 8) blocksPerSm = 8;
   if (blocksPerSm < 1) blocksPerSm = 1;
+  // small scenes: stackless traversal of the threaded tree (exact mode only; the stats variant counts in the
+  // stack kernel, whose tests are the same ones)
+  const bool threaded = sc.tnodes != nullptr;
+  const size_t smemTrace = threaded ? (size_t)LT_MAX_BATCH * LT_BLOCK * sizeof(int) : smem;
+  LtLaunch Lt = L;  // iteration shape of the trace kernel: single-box steps when threaded
+  if (threaded) {
+    blocksPerSm = lt_env_int("LT_THREADED_BLOCKS_PER_SM", 8);
+    Lt.iterNodeSteps = lt_env_int("LT_THREADED_NODE_STEPS", 2 * L.iterNodeSteps);
+    Lt.iterTriTests = lt_env_int("LT_THREADED_TRI_TESTS", L.iterTriTests);
+  }
   const int persistentBlocks = smCount * blocksPerSm;
   int launches = 0;
   for (int frame0 = 0; frame0 < L.frames; frame0 += batchFrames) {
@@ -390,8 +417,13 @@ int lt_launch_render_wavefront(const LtSceneDev& sc, const LtLaunch& L, float* d
       int q = 0;
       for (int r = 1; r < rounds; r++) {
         mark(0);
-        if (stats) k_wf_trace<true><<<persistentBlocks, WF_BLOCK, smem, stream>>>(sc, Lb, B, q, dCounters);
-        else k_wf_trace<false><<<persistentBlocks, WF_BLOCK, smem, stream>>>(sc, Lb, B, q, nullptr);
+        if (stats) k_wf_trace<true, false><<<persistentBlocks, WF_BLOCK, smem, stream>>>(sc, Lb, B, q, dCounters);
+        else if (threaded) {
+          LtLaunch Lq = Lb;
+          Lq.iterNodeSteps = Lt.iterNodeSteps;
+          Lq.iterTriTests = Lt.iterTriTests;
+          k_wf_trace<false, true><<<persistentBlocks, WF_BLOCK, smemTrace, stream>>>(sc, Lq, B, q, nullptr);
+        } else k_wf_trace<false, false><<<persistentBlocks, WF_BLOCK, smem, stream>>>(sc, Lb, B, q, nullptr);
         mark(1);
         k_wf_shade<<<grid, WF_BLOCK, 0, stream>>>(sc, Lb, B, q, pixels, 0, s);
         k_wf_swap<<<1, 1, 0, stream>>>(B, q);

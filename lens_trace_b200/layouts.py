@@ -36,6 +36,7 @@ FLAG_STATS = 1
 FLAG_CULL = 2
 FLAG_MEGAKERNEL = 4
 FLAG_WAVEFRONT = 8
+FLAG_NO_THREADED = 16  # small scenes: stack kernels instead of the stackless threaded tree (same output)
 
 
 def make_camera(x, y, z, yaw=0.0, frame_count=0):

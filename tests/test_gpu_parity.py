@@ -79,7 +79,9 @@ def test_reference_known_answer_on_gpu(ctx):
         assert flat[x] == 0.0 and flat[x + 1] == 1.0 and flat[x + 2] == 0.0
 
 
-PIPES = [L.FLAG_MEGAKERNEL, L.FLAG_WAVEFRONT]  # the two schedules of the stochastic kernels: identical output
+# the schedules of the stochastic kernels (identical output): persistent megakernel, wavefront with the stackless
+# threaded traversal (small scenes), wavefront with the stack traversal
+PIPES = [L.FLAG_MEGAKERNEL, L.FLAG_WAVEFRONT, L.FLAG_WAVEFRONT | L.FLAG_NO_THREADED]
 
 
 @pytest.mark.parametrize("pipe", PIPES)
@@ -195,6 +197,25 @@ def test_stats_mode_does_not_change_the_image(ctx):
     util.assert_bit_equal(a, b)
 
 
+def test_leaf_fifo_capacity_on_a_deep_tree(ctx, tmp_path):
+    """Regression: one step of the stack traversal can record three leaves (near, far, and one popped behind
+    them); with room for only two the FIFO overwrote its oldest entry -- one pixel of this 1080p frame.  All
+    schedules must agree, and agree with the oracle on the rows around that pixel."""
+    from lens_trace_b200 import host
+    p = str(tmp_path / "synth.obj")
+    host.write_synthetic_scene(p, 96, 0x5EED)
+    sb = host.load_scene_buffers(p)
+    sc = ctx.upload(sb)
+    cam = util.default_camera(0.0, 8)
+    imgs = [ctx.render(sc, cam, capi.make_params(L.KERNEL_GI, 1920, 1080, max_ray_depth=4, flags=pipe)).copy()
+            for pipe in PIPES]
+    sc.release()
+    util.assert_bit_equal(imgs[1], imgs[0], "wavefront threaded vs megakernel")
+    util.assert_bit_equal(imgs[2], imgs[0], "wavefront stack vs megakernel")
+    want = O.render(L.KERNEL_GI, sb, cam, 1920, 1080, max_ray_depth=4, rows=(540, 548), threads=0)
+    assert_images_match(imgs[2][540:548], want[540:548], "rows 540..547 vs oracle", max_outliers=3)
+
+
 def test_synthetic_mesh_parity(ctx, tmp_path):
     from lens_trace_b200 import host
     p = str(tmp_path / "synth.obj")
@@ -207,9 +228,10 @@ def test_synthetic_mesh_parity(ctx, tmp_path):
     np.testing.assert_array_equal(hit, ohit)
     np.testing.assert_array_equal(ids, oids)
     util.assert_bit_equal(tuv, otuv)
-    got = ctx.render(sc, util.default_camera(0.0, 3), capi.make_params(L.KERNEL_GI, 160, 90, max_ray_depth=4))
     want = O.render(L.KERNEL_GI, sb, util.default_camera(0.0, 3), 160, 90, max_ray_depth=4, threads=0)
-    assert_images_match(got, want, "synthetic GI", max_outliers=3)
+    for pipe in [0] + PIPES:  # default choice, megakernel, wavefront threaded (36 887 nodes), wavefront stack
+        got = ctx.render(sc, util.default_camera(0.0, 3), capi.make_params(L.KERNEL_GI, 160, 90, max_ray_depth=4, flags=pipe))
+        assert_images_match(got, want, "synthetic GI, flags %d" % pipe, max_outliers=3)
     sc.release()
 
 
