@@ -66,6 +66,8 @@ enum lt_flags {
   LT_FLAG_MEGAKERNEL = 1 << 2, /* stochastic kernels: force the one-thread-per-pixel persistent kernel */
   LT_FLAG_WAVEFRONT = 1 << 3,  /* stochastic kernels: force the wavefront pipeline (default: chosen by size;
                                   both produce bit-identical output) */
+  LT_FLAG_SERIAL = 1 << 5,     /* wavefront pipeline: one stream, one kernel at a time (default: consecutive batches
+                                  overlap on two streams; identical output).  For timing kernels in isolation. */
   LT_FLAG_NO_THREADED = 1 << 4 /* small scenes: traverse with the stack kernels instead of the stackless threaded
                                   tree (default for scenes whose 8 octant copies stay cache resident; identical
                                   output, kept selectable so tests can compare the two) */

@@ -23,8 +23,9 @@ struct lt_ctx {
   std::vector<cudaEvent_t> traceEvents;  // pairs of events around traversal launches (timed when synchronous)
   std::vector<LtPlugin*> plugins;  // compiled user kernels, by id
   RefCamera* dCamera = nullptr;    // camera buffer for plug-in launches
-  void* wfWorkspace = nullptr;  // wavefront path state / ray queues
+  void* wfWorkspace = nullptr;  // wavefront path state / ray queues (two batch workspaces when batches overlap)
   size_t wfBytes = 0;
+  LtWfAux wfAux = {};           // second stream + events for overlapping consecutive wavefront batches
   size_t totalMem = 0;
   lt_stats stats = {};
 };
@@ -86,6 +87,11 @@ extern "C" int lt_ctx_create(int device_ordinal, lt_ctx** out_ctx) {
   if (e2 == cudaSuccess) e2 = cudaEventCreate(&ctx->ev0);
   if (e2 == cudaSuccess) e2 = cudaEventCreate(&ctx->ev1);
   if (e2 == cudaSuccess) e2 = cudaMalloc(&ctx->dCounters, sizeof(LtCounters));
+  for (int k = 1; k < LT_WF_MAX_STREAMS; k++)
+    if (e2 == cudaSuccess) e2 = cudaStreamCreateWithFlags(&ctx->wfAux.extra[k], cudaStreamNonBlocking);
+  if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&ctx->wfAux.fork, cudaEventDisableTiming);
+  for (int k = 0; k < LT_WF_MAX_STREAMS; k++)
+    if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&ctx->wfAux.order[k], cudaEventDisableTiming);
   if (e2 != cudaSuccess) {
     std::string m = std::string("lt_ctx_create: ") + cudaGetErrorString(e2);
     delete ctx;
@@ -108,6 +114,14 @@ extern "C" void lt_ctx_destroy(lt_ctx* ctx) {
   for (cudaEvent_t e : ctx->traceEvents) cudaEventDestroy(e);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  for (int k = 1; k < LT_WF_MAX_STREAMS; k++)
+    if (ctx->wfAux.extra[k]) {
+      cudaStreamSynchronize(ctx->wfAux.extra[k]);
+      cudaStreamDestroy(ctx->wfAux.extra[k]);
+    }
+  if (ctx->wfAux.fork) cudaEventDestroy(ctx->wfAux.fork);
+  for (int k = 0; k < LT_WF_MAX_STREAMS; k++)
+    if (ctx->wfAux.order[k]) cudaEventDestroy(ctx->wfAux.order[k]);
   if (ctx->ownStream) cudaStreamDestroy(ctx->ownStream);
   delete ctx;
 }
@@ -499,7 +513,7 @@ static int render_common(lt_ctx* ctx, lt_scene* scene, const LtLaunch& L, float*
   bool stats = (L.flags & LT_FLAG_STATS) != 0;
   if (stats) CK(cudaMemsetAsync(ctx->dCounters, 0, sizeof(LtCounters), ctx->stream));
   // stochastic kernels: wavefront pipeline for large launches, persistent megakernel for small ones
-  bool wavefront = false;
+  bool wavefront = false, overlapBatches = false;
   int batchFrames = 1;
   if (L.kernel >= 3 && !(L.flags & LT_FLAG_MEGAKERNEL)) {
     long long pixels = (long long)L.width * L.height;
@@ -508,7 +522,7 @@ static int render_common(lt_ctx* ctx, lt_scene* scene, const LtLaunch& L, float*
       const char* e = getenv("LT_WAVEFRONT_MIN_PATHS");
       minPaths = e ? atoll(e) : (1ll << 23);
       e = getenv("LT_WAVEFRONT_MAX_PATHS");
-      maxPaths = e ? atoll(e) : (1ll << 24);
+      maxPaths = e ? atoll(e) : (1ll << 25);  // paths in flight, all overlapped batches together (~200 B each)
     }
     // measured (tools/compare_pipelines.py): the wavefront wins once ~8M paths are in flight per batch; below
     // that, and for the two-ray lighting kernels on small scenes, its per-round launches and state traffic lose
@@ -523,7 +537,23 @@ static int render_common(lt_ctx* ctx, lt_scene* scene, const LtLaunch& L, float*
       batchFrames = (int)(cap / pixels);
       if (batchFrames < 1) batchFrames = 1;
       if (batchFrames > L.frames) batchFrames = L.frames;
-      size_t need = lt_wf_workspace_bytes_padded((long long)batchFrames * pixels);
+      // consecutive batches overlap on LT_WF_OVERLAP (default 2) streams (trace of one beside shade of another): smaller batches,
+      // one workspace each -- same memory.  LT_FLAG_SERIAL / LT_WF_OVERLAP=1: one stream, kernels run one at a time.
+      static int overlapEnv = -1;
+      if (overlapEnv < 0) {
+        const char* e = getenv("LT_WF_OVERLAP");
+        overlapEnv = e ? atoi(e) : 2;  // batches in flight
+      }
+      overlapBatches = overlapEnv >= 2 && !(L.flags & (LT_FLAG_SERIAL | LT_FLAG_STATS)) && L.frames >= 2;
+      int nStreams = 1;
+      if (overlapBatches) {
+        nStreams = overlapEnv > LT_WF_MAX_STREAMS ? LT_WF_MAX_STREAMS : overlapEnv;
+        if (nStreams > L.frames) nStreams = L.frames;
+        if (batchFrames >= nStreams) batchFrames = (batchFrames + nStreams - 1) / nStreams;
+        else batchFrames = 1;
+        ctx->wfAux.streams = nStreams;
+      }
+      size_t need = lt_wf_workspace_bytes_padded((long long)batchFrames * pixels) * (size_t)nStreams;
       if (ctx->wfBytes < need) {
         if (ctx->wfWorkspace) cudaFree(ctx->wfWorkspace);
         ctx->wfWorkspace = nullptr;
@@ -550,7 +580,7 @@ static int render_common(lt_ctx* ctx, lt_scene* scene, const LtLaunch& L, float*
   int launches = wavefront ? lt_launch_render_wavefront(scene->dev, L, dOut, ctx->dCounters, ctx->wfWorkspace,
                                                         batchFrames, ctx->stats.sm_count, ctx->stream,
                                                         timeTrace ? ctx->traceEvents.data() : nullptr, kMaxTracePairs,
-                                                        &tracePairs)
+                                                        &tracePairs, overlapBatches ? &ctx->wfAux : nullptr)
                            : lt_launch_render(scene->dev, L, dOut, ctx->dCounters, ctx->stream);
   CK(cudaGetLastError());
   CK(cudaEventRecord(ctx->ev1, ctx->stream));

@@ -46,9 +46,20 @@ int lt_launch_debug_hemisphere(const float* u1, const float* u2, const float* up
 size_t lt_wf_workspace_bytes_padded(long long nPaths);
 // traceEvents: optional pool of 2*maxTraceLaunches events; when given, every traversal launch is bracketed by a
 // pair of events and *traceLaunches receives the number of pairs recorded
+// aux: extra streams + events (fork, one batch-order event per stream) for overlapping consecutive batches (the
+// L1-bound trace kernel of one batch runs beside the DRAM-bound shade kernel of another and fills the tail of the
+// persistent kernels); `workspace` then holds aux->streams
+// batch workspaces of lt_wf_workspace_bytes_padded(batchFrames * pixels) each.  aux == nullptr: one stream.
+#define LT_WF_MAX_STREAMS 4
+struct LtWfAux {
+  int streams;                              // batches in flight (2..LT_WF_MAX_STREAMS), one stream each
+  cudaStream_t extra[LT_WF_MAX_STREAMS];    // [0] unused: side 0 runs on the caller's stream
+  cudaEvent_t fork, order[LT_WF_MAX_STREAMS];
+};
 int lt_launch_render_wavefront(const LtSceneDev& sc, const LtLaunch& L, float* dOut, LtCounters* dCounters,
                                void* workspace, int batchFrames, int smCount, cudaStream_t stream,
-                               cudaEvent_t* traceEvents, int maxTraceLaunches, int* traceLaunches);
+                               cudaEvent_t* traceEvents, int maxTraceLaunches, int* traceLaunches,
+                               const LtWfAux* aux);
 
 // user-written CUDA kernels with the reference's plug-in ABI (lt_plugin.cu)
 #include <string>

@@ -368,12 +368,13 @@ size_t lt_wf_workspace_bytes_padded(long long nPaths) {
 
 int lt_launch_render_wavefront(const LtSceneDev& scIn, const LtLaunch& L, float* dOut, LtCounters* dCounters,
                                void* workspace, int batchFrames, int smCount, cudaStream_t stream,
-                               cudaEvent_t* traceEvents, int maxTraceLaunches, int* traceLaunches) {
+                               cudaEvent_t* traceEvents, int maxTraceLaunches, int* traceLaunches,
+                               const LtWfAux* aux) {
   LtSceneDev sc = scIn;
   if (L.flags & (1 | 2 | LT_LAUNCH_FLAG_NO_THREADED)) sc.tnodes = nullptr;  // stats / culled / forced stack traversal
   int pairs = 0;
-  auto mark = [&](int which) {  // which: 0 = before, 1 = after a traversal launch
-    if (traceEvents && pairs < maxTraceLaunches) cudaEventRecord(traceEvents[2 * pairs + which], stream);
+  auto mark = [&](int which, cudaStream_t s) {  // which: 0 = before, 1 = after a traversal launch
+    if (traceEvents && pairs < maxTraceLaunches) cudaEventRecord(traceEvents[2 * pairs + which], s);
     if (which == 1 && traceEvents && pairs < maxTraceLaunches) pairs++;
   };
   const int pixels = L.width * L.height;
@@ -396,44 +397,66 @@ int lt_launch_render_wavefront(const LtSceneDev& scIn, const LtLaunch& L, float*
     Lt.iterNodeSteps = lt_env_int("LT_THREADED_NODE_STEPS", 2 * L.iterNodeSteps);
     Lt.iterTriTests = lt_env_int("LT_THREADED_TRI_TESTS", L.iterTriTests);
   }
+  // Two batches in flight on two streams: the persistent trace kernel leaves room on every SM for blocks of the
+  // other batch's shade kernel (different bottlenecks: L1 data pipe vs DRAM).
+  const bool overlap = aux != nullptr && L.frames > batchFrames;
+  const int nStreams = overlap ? aux->streams : 1;
+  if (overlap) {  // measured: reserving room for the other batch's blocks (fewer persistent blocks) does not pay
+    int cap = lt_env_int("LT_WF_OVERLAP_TRACE_BLOCKS_PER_SM", 8);
+    if (blocksPerSm > cap) blocksPerSm = cap;
+  }
   const int persistentBlocks = smCount * blocksPerSm;
-  int launches = 0;
-  for (int frame0 = 0; frame0 < L.frames; frame0 += batchFrames) {
+  const size_t wsBytes = lt_wf_workspace_bytes_padded((long long)batchFrames * pixels);
+  if (overlap) {
+    cudaEventRecord(aux->fork, stream);
+    for (int k = 1; k < nStreams; k++) cudaStreamWaitEvent(aux->extra[k], aux->fork, 0);
+  }
+  int launches = 0, batch = 0, lastSide = 0;
+  for (int frame0 = 0; frame0 < L.frames; frame0 += batchFrames, batch++) {
+    const int side = overlap ? (batch % nStreams) : 0;
+    cudaStream_t st = side ? aux->extra[side] : stream;
     int nf = L.frames - frame0 < batchFrames ? L.frames - frame0 : batchFrames;
     long long nPaths = (long long)nf * pixels;
-    LtWfBuffers B = carve(workspace, (long long)batchFrames * pixels);
+    LtWfBuffers B = carve((char*)workspace + (size_t)side * wsBytes, (long long)batchFrames * pixels);
     LtLaunch Lb = L;
     Lb.cam.frameCount = L.cam.frameCount + (unsigned)frame0 * L.frameStride;  // frame index 0 of the batch
     int grid = (int)((nPaths + WF_BLOCK - 1) / WF_BLOCK);
     if (grid > smCount * 32) grid = smCount * 32;
     for (int s = 0; s < samples; s++) {
       // round 0 (primary rays) fused into one kernel; its survivors are queue 0
-      k_wf_reset<<<1, 1, 0, stream>>>(B);
-      mark(0);
-      if (stats) k_wf_primary<true><<<grid, WF_BLOCK, smem, stream>>>(sc, Lb, B, nPaths, pixels, s, dCounters);
-      else k_wf_primary<false><<<grid, WF_BLOCK, smem, stream>>>(sc, Lb, B, nPaths, pixels, s, nullptr);
-      mark(1);
+      k_wf_reset<<<1, 1, 0, st>>>(B);
+      mark(0, st);
+      if (stats) k_wf_primary<true><<<grid, WF_BLOCK, smem, st>>>(sc, Lb, B, nPaths, pixels, s, dCounters);
+      else k_wf_primary<false><<<grid, WF_BLOCK, smem, st>>>(sc, Lb, B, nPaths, pixels, s, nullptr);
+      mark(1, st);
       launches += 2;
       int q = 0;
       for (int r = 1; r < rounds; r++) {
-        mark(0);
-        if (stats) k_wf_trace<true, false><<<persistentBlocks, WF_BLOCK, smem, stream>>>(sc, Lb, B, q, dCounters);
+        mark(0, st);
+        if (stats) k_wf_trace<true, false><<<persistentBlocks, WF_BLOCK, smem, st>>>(sc, Lb, B, q, dCounters);
         else if (threaded) {
           LtLaunch Lq = Lb;
           Lq.iterNodeSteps = Lt.iterNodeSteps;
           Lq.iterTriTests = Lt.iterTriTests;
-          k_wf_trace<false, true><<<persistentBlocks, WF_BLOCK, smemTrace, stream>>>(sc, Lq, B, q, nullptr);
-        } else k_wf_trace<false, false><<<persistentBlocks, WF_BLOCK, smem, stream>>>(sc, Lb, B, q, nullptr);
-        mark(1);
-        k_wf_shade<<<grid, WF_BLOCK, 0, stream>>>(sc, Lb, B, q, pixels, 0, s);
-        k_wf_swap<<<1, 1, 0, stream>>>(B, q);
+          k_wf_trace<false, true><<<persistentBlocks, WF_BLOCK, smemTrace, st>>>(sc, Lq, B, q, nullptr);
+        } else k_wf_trace<false, false><<<persistentBlocks, WF_BLOCK, smem, st>>>(sc, Lb, B, q, nullptr);
+        mark(1, st);
+        k_wf_shade<<<grid, WF_BLOCK, 0, st>>>(sc, Lb, B, q, pixels, 0, s);
+        k_wf_swap<<<1, 1, 0, st>>>(B, q);
         launches += 3;
         q = 1 - q;
       }
     }
-    k_wf_accumulate<<<(pixels + WF_BLOCK - 1) / WF_BLOCK, WF_BLOCK, 0, stream>>>(L, B, dOut, pixels, frame0, nf);
+    // the frame combiner is applied in frame order: this batch's accumulate follows the previous batch's
+    if (overlap && batch > 0) cudaStreamWaitEvent(st, aux->order[(side + nStreams - 1) % nStreams], 0);
+    k_wf_accumulate<<<(pixels + WF_BLOCK - 1) / WF_BLOCK, WF_BLOCK, 0, st>>>(L, B, dOut, pixels, frame0, nf);
+    if (overlap) cudaEventRecord(aux->order[side], st);
+    lastSide = side;
     launches++;
   }
+  // join: the last accumulate follows every earlier one (chain of order events), and every stream's last kernel is
+  // its accumulate, so waiting for the last batch's event puts all of it before what follows on `stream`
+  if (overlap && lastSide != 0) cudaStreamWaitEvent(stream, aux->order[lastSide], 0);
   if (traceLaunches) *traceLaunches = pairs;
   return launches;
 }

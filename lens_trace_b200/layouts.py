@@ -36,6 +36,7 @@ FLAG_STATS = 1
 FLAG_CULL = 2
 FLAG_MEGAKERNEL = 4
 FLAG_WAVEFRONT = 8
+FLAG_SERIAL = 32  # wavefront: no overlap of consecutive batches (timing kernels in isolation; same output)
 FLAG_NO_THREADED = 16  # small scenes: stack kernels instead of the stackless threaded tree (same output)
 
 
