@@ -325,6 +325,14 @@ def main():
     if world > 1:
         dist.all_reduce(counts)
     rays, node_tests, tri_tests = [float(x) for x in counts.tolist()]
+    # The camera ray of a pixel is the same in every frame (the reference has no sub-pixel jitter), so the wavefront
+    # pipeline traces it once per pixel per step and starts all `frames` paths of the pixel from that hit record.
+    # rays / node_tests / tri_tests above are the reference's counts (one primary ray per pixel per frame); the
+    # traversal kernels actually execute (frames - 1) primary rays per pixel fewer.  Counted with the primary-only
+    # kernel (basic.cl: one camera ray per pixel; the bench scenes have no lens material).
+    ctx.render_device(scene, cam, capi.make_params(L.KERNEL_BASIC_CL, w, h, flags=L.FLAG_STATS), acc.data_ptr(), sync=True)
+    sp = ctx.stats()
+    primary_counts = (float(sp.rays), float(sp.node_tests), float(sp.tri_tests))
 
     for _ in range(max(3, args.warmup)):
         step()
@@ -344,23 +352,38 @@ def main():
         e0.record(stream)
         if world > 1:
             acc.zero_()
-        # synchronous call: the library brackets every traversal launch with its own CUDA events on this
-        # stream and sums them (lt_stats.trace_ms) -- the live duration of the dominant kernels
-        ctx.render_device(scene, cam, make_step_params(), acc.data_ptr(), sync=True)
+        ctx.render_device(scene, cam, make_step_params(), acc.data_ptr(), sync=False)
         e1.record(stream)
         if world > 1:
             dist.all_reduce(acc)
         e2.record(stream)
         events.append((e0, e2))
         kernel_events.append((e0, e1))
-        st_step = ctx.stats()
-        trace_ms_total += st_step.trace_ms
-        trace_launches += st_step.trace_launches
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     clocks = sampler.summary()
     launches_per_step = ctx.stats().kernel_launches
+    # The dominant kernels timed in isolation, live, for the roofline: in the timed steps above consecutive batches
+    # of the wavefront pipeline overlap on two streams (a trace kernel beside another batch's shade kernel), so a
+    # launch's own duration is only defined with the overlap off (LT_FLAG_SERIAL: same kernels, same output, one
+    # stream).  Synchronous call: the library brackets every traversal launch with CUDA events on this stream and
+    # sums them (lt_stats.trace_ms).
+    iso_steps = max(1, min(args.steps, 3))
+    iso_pipeline_ms = 0.0
+    for _ in range(iso_steps):
+        flush.fill_(1.0)
+        if world > 1:
+            acc.zero_()
+        ctx.render_device(scene, cam, make_step_params(L.FLAG_SERIAL), acc.data_ptr(), sync=True)
+        st_step = ctx.stats()
+        trace_ms_total += st_step.trace_ms
+        trace_launches += st_step.trace_launches
+        iso_pipeline_ms += st_step.kernel_ms
+    if world > 1:
+        acc.zero_()
+        ctx.render_device(scene, cam, make_step_params(), acc.data_ptr(), sync=True)  # leave acc as a step leaves it
+        dist.all_reduce(acc)
     total_ms = sum(a.elapsed_time(b) for a, b in events)
     kernel_ms = sum(a.elapsed_time(b) for a, b in kernel_events)
     t = torch.tensor([total_ms, kernel_ms], dtype=torch.float64, device=dev)
@@ -398,10 +421,18 @@ def main():
         sm_count = st.sm_count or 148
         fp32_peak = sm_count * 128 * pk["sm_max_mhz"] * 1e6  # lane-instructions / s
         # roofline of ONE GPU's kernels: the counters were summed over ranks
-        alg_instr = (12.0 * node_tests + 45.0 * tri_tests) / world
-        alg_bytes = (32.0 * node_tests + 36.0 * tri_tests) / world
+        shared_primary = launches_per_step > 1 and frames > 1  # the wavefront pipeline (exact mode) does this
+        skipped = (frames - 1) * world if shared_primary else 0
+        rays_traced = rays - skipped * primary_counts[0]
+        node_traced = node_tests - skipped * primary_counts[1]
+        tri_traced = tri_tests - skipped * primary_counts[2]
+        # algorithmic work of the rays the timed traversal launches actually trace (32 B and 12
+        # lane-instructions per box test, 36 B and 45 per triangle test, counted in the reference's traversal order)
+        alg_instr = (12.0 * node_traced + 45.0 * tri_traced) / world
+        alg_bytes = (32.0 * node_traced + 36.0 * tri_traced) / world
+        ref_alg_bytes = (32.0 * node_tests + 36.0 * tri_tests) / world
         # the dominant kernels are the traversal kernels; their summed duration per step, measured live
-        trace_s = trace_ms_total / args.steps * 1e-3
+        trace_s = trace_ms_total / iso_steps * 1e-3
         k_s = trace_s if trace_s > 0 else kernel_ms / args.steps * 1e-3
         scene_bytes = sb.nodes.nbytes + sb.prims.nbytes
         level = "hbm" if scene_bytes > 126e6 else ("l2" if scene_bytes > 200e3 else "l1")
@@ -432,14 +463,23 @@ def main():
         roof.update({"kernel": "k_wf_primary + k_wf_trace (traversal kernels of the wavefront pipeline)"
                      if launches_per_step > 1 else pipeline,
                      "pipeline": pipeline,
-                     "traversal_ms_per_step": trace_ms_total / args.steps,
-                     "traversal_launches_per_step": trace_launches / args.steps,
+                     "timing": "traversal launches timed live with CUDA events, kernels in isolation (LT_FLAG_SERIAL: "
+                               "one stream, %d steps); the timed steps overlap consecutive batches on two streams" % iso_steps,
+                     "traversal_ms_per_step": trace_ms_total / iso_steps,
+                     "traversal_launches_per_step": trace_launches / iso_steps,
                      "traversal_avg_launch_ms": trace_ms_total / max(1, trace_launches),
-                     "traversal_share_of_step": trace_ms_total / max(1e-9, kernel_ms),
+                     "traversal_share_of_step": trace_ms_total / max(1e-9, iso_pipeline_ms),
+                     "pipeline_ms_per_step_in_isolation": iso_pipeline_ms / iso_steps,
                      "pipeline_ms_per_step": kernel_ms / args.steps,
                      "kernels_per_step": launches_per_step,
-                     "algorithmic_units": "per step (all traversal launches of one step), per GPU",
+                     "algorithmic_units": "per step (all traversal launches of one step), per GPU; rays actually traced",
                      "algorithmic_bytes_per_step": alg_bytes, "algorithmic_fp32_instr_per_step": alg_instr,
+                     "rays_traced_per_step": rays_traced / world,
+                     "reference_rays_per_step": rays / world,
+                     "reference_algorithmic_bytes_per_step": ref_alg_bytes,
+                     "primary_rays": "traced once per pixel per step and shared by the step's %d frames "
+                                     "(identical camera ray in every frame); value counts the reference's rays" % frames
+                     if shared_primary else "one per pixel per frame",
                      "node_tests_per_ray": node_tests / rays, "tri_tests_per_ray": tri_tests / rays,
                      "fp32_issue": fp32, "node_fetch": fetch,
                      "hbm_view": {"achieved": alg_bytes / k_s / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",

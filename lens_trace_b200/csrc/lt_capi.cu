@@ -553,7 +553,8 @@ static int render_common(lt_ctx* ctx, lt_scene* scene, const LtLaunch& L, float*
         else batchFrames = 1;
         ctx->wfAux.streams = nStreams;
       }
-      size_t need = lt_wf_workspace_bytes_padded((long long)batchFrames * pixels) * (size_t)nStreams;
+      size_t need = lt_wf_workspace_bytes_padded((long long)batchFrames * pixels) * (size_t)nStreams +
+                    lt_wf_primary_hits_bytes(pixels);
       if (ctx->wfBytes < need) {
         if (ctx->wfWorkspace) cudaFree(ctx->wfWorkspace);
         ctx->wfWorkspace = nullptr;

@@ -44,6 +44,7 @@ int lt_launch_debug_hemisphere(const float* u1, const float* u2, const float* up
 
 // wavefront pipeline (lt_wavefront.cu)
 size_t lt_wf_workspace_bytes_padded(long long nPaths);
+size_t lt_wf_primary_hits_bytes(long long pixels);  // per-launch primary hit records, kept behind the batch workspaces
 // traceEvents: optional pool of 2*maxTraceLaunches events; when given, every traversal launch is bracketed by a
 // pair of events and *traceLaunches receives the number of pairs recorded
 // aux: extra streams + events (fork, one batch-order event per stream) for overlapping consecutive batches (the

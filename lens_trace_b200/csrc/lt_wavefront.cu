@@ -85,9 +85,29 @@ __device__ __forceinline__ unsigned sample_index_of(const LtLaunch& L, const Pat
 // Round 0 fused: camera ray -> trace -> shade for every path of the batch.  Primary rays are coherent
 // (neighbouring pixels), so one ray per thread is efficient here, and no ray/hit record of the primary
 // round ever touches memory; paths that end at once (miss, light hit) only deposit their colour.
+// The camera ray of a pixel is the same in every frame and sample of a launch (no sub-pixel jitter anywhere in the
+// reference, basic.cu:350-358), so its hit is traced once per pixel per launch and every (pixel, frame) path of
+// every batch starts from that record: exactly the hit each of them would have found.
+__global__ void __launch_bounds__(WF_BLOCK) k_wf_primary_trace(LtSceneDev sc, LtLaunch L, float4* __restrict__ hits,
+                                                               int pixels) {
+  LT_SMEM_POINTERS(sc)
+  (void)tstk;
+  int pixel = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pixel >= pixels) return;
+  int py = pixel / L.width, px = pixel - py * L.width;
+  float fx, fy;
+  Trav t;
+  t.r = camera_ray(L.cam, px, py, L.width, L.height, fx, fy);
+  LtCounters cnt = {0, 0, 0};
+  trace<false>(t, sc, -1, lt_tinit(L.kernel), lt_eps(L.kernel), false, stk, list, cnt);
+  hits[pixel] = make_float4(t.h.t, t.h.u, t.h.v, __int_as_float((int)((unsigned)t.h.prim | (t.h.hit ? 0x80000000u : 0u))));
+}
+
+// primaryHits != nullptr: the per-pixel records of k_wf_primary_trace replace the trace (exact, uncounted launches)
 template <bool STATS>
 __global__ void __launch_bounds__(WF_BLOCK) k_wf_primary(LtSceneDev sc, LtLaunch L, LtWfBuffers B, long long nPaths,
-                                                         int pixels, int sample, LtCounters* gcnt) {
+                                                         int pixels, int sample, LtCounters* gcnt,
+                                                         const float4* __restrict__ primaryHits) {
   LT_SMEM_POINTERS(sc)
   const bool cull = (L.flags & 2) != 0;  // LT_FLAG_CULL: closest-hit rays skip subtrees behind the current hit
   const PathConsts pc = path_consts(L);
@@ -106,9 +126,22 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_primary(LtSceneDev sc, LtLaunch
       int px, py, fl;
       pixel_of_path(p, pixels, L.width, px, py, fl);
       float fx, fy;
-      t.r = camera_ray(L.cam, px, py, L.width, L.height, fx, fy);
-      if (cull) trace_cull<STATS>(t, sc, -1, pc.tInit, pc.epsThr, stk, tstk, cnt);
-      else trace<STATS>(t, sc, -1, pc.tInit, pc.epsThr, false, stk, list, cnt);
+      if (!STATS && primaryHits != nullptr) {
+        fx = FADD(FDIV((float)px, (float)L.width), -0.5f);  // the film position camera_ray computes
+        fy = FADD(FDIV((float)py, (float)L.height), -0.5f);
+        float4 hv = primaryHits[(int)(p - (long long)fl * pixels)];
+        unsigned hb = (unsigned)__float_as_int(hv.w);
+        t.h.t = hv.x; t.h.u = hv.y; t.h.v = hv.z;
+        t.h.prim = (int)(hb & 0x7fffffffu);
+        t.h.hit = (int)(hb >> 31);
+        t.r.ox = t.r.oy = t.r.oz = 0.0f;  // a primary hit is shaded from its hit record alone (shade_step, ST_PRIMARY)
+        t.r.dx = t.r.dy = 0.0f;
+        t.r.dz = 1.0f;
+      } else {
+        t.r = camera_ray(L.cam, px, py, L.width, L.height, fx, fy);
+        if (cull) trace_cull<STATS>(t, sc, -1, pc.tInit, pc.epsThr, stk, tstk, cnt);
+        else trace<STATS>(t, sc, -1, pc.tInit, pc.epsThr, false, stk, list, cnt);
+      }
       PathState ps;
       ps.nrm[0] = ps.nrm[1] = ps.nrm[2] = 0.0f;
       ps.diffuse[0] = ps.diffuse[1] = ps.diffuse[2] = 0.0f;
@@ -366,6 +399,8 @@ size_t lt_wf_workspace_bytes_padded(long long nPaths) {
   return lt_wf_workspace_bytes(nPaths) + 256 * 16;
 }
 
+size_t lt_wf_primary_hits_bytes(long long pixels) { return sizeof(float4) * (size_t)pixels + 256; }
+
 int lt_launch_render_wavefront(const LtSceneDev& scIn, const LtLaunch& L, float* dOut, LtCounters* dCounters,
                                void* workspace, int batchFrames, int smCount, cudaStream_t stream,
                                cudaEvent_t* traceEvents, int maxTraceLaunches, int* traceLaunches,
@@ -407,11 +442,21 @@ int lt_launch_render_wavefront(const LtSceneDev& scIn, const LtLaunch& L, float*
   }
   const int persistentBlocks = smCount * blocksPerSm;
   const size_t wsBytes = lt_wf_workspace_bytes_padded((long long)batchFrames * pixels);
+  int preLaunches = 0;
+  // primary hits once per pixel per launch (exact, uncounted pipelines); kept behind the batch workspaces
+  float4* primaryHits = nullptr;
+  if (!stats && !(L.flags & 2) && lt_env_int("LT_WF_SHARED_PRIMARY", 1)) {
+    primaryHits = (float4*)((char*)workspace + (size_t)nStreams * wsBytes);
+    mark(0, stream);
+    k_wf_primary_trace<<<(pixels + WF_BLOCK - 1) / WF_BLOCK, WF_BLOCK, smem, stream>>>(sc, L, primaryHits, pixels);
+    mark(1, stream);
+    preLaunches = 1;
+  }
   if (overlap) {
     cudaEventRecord(aux->fork, stream);
     for (int k = 1; k < nStreams; k++) cudaStreamWaitEvent(aux->extra[k], aux->fork, 0);
   }
-  int launches = 0, batch = 0, lastSide = 0;
+  int launches = preLaunches, batch = 0, lastSide = 0;
   for (int frame0 = 0; frame0 < L.frames; frame0 += batchFrames, batch++) {
     const int side = overlap ? (batch % nStreams) : 0;
     cudaStream_t st = side ? aux->extra[side] : stream;
@@ -425,10 +470,10 @@ int lt_launch_render_wavefront(const LtSceneDev& scIn, const LtLaunch& L, float*
     for (int s = 0; s < samples; s++) {
       // round 0 (primary rays) fused into one kernel; its survivors are queue 0
       k_wf_reset<<<1, 1, 0, st>>>(B);
-      mark(0, st);
-      if (stats) k_wf_primary<true><<<grid, WF_BLOCK, smem, st>>>(sc, Lb, B, nPaths, pixels, s, dCounters);
-      else k_wf_primary<false><<<grid, WF_BLOCK, smem, st>>>(sc, Lb, B, nPaths, pixels, s, nullptr);
-      mark(1, st);
+      if (!primaryHits) mark(0, st);  // a traversal kernel only when it traces the camera rays itself
+      if (stats) k_wf_primary<true><<<grid, WF_BLOCK, smem, st>>>(sc, Lb, B, nPaths, pixels, s, dCounters, nullptr);
+      else k_wf_primary<false><<<grid, WF_BLOCK, smem, st>>>(sc, Lb, B, nPaths, pixels, s, nullptr, primaryHits);
+      if (!primaryHits) mark(1, st);
       launches += 2;
       int q = 0;
       for (int r = 1; r < rounds; r++) {
