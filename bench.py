@@ -426,6 +426,11 @@ def main():
         rays_traced = rays - skipped * primary_counts[0]
         node_traced = node_tests - skipped * primary_counts[1]
         tri_traced = tri_tests - skipped * primary_counts[2]
+        if kernel <= 2 and frames > 1:
+            # deterministic kernels: every frame is the same image, k_flat traces once and applies the frame
+            # combiner `frames` times in registers
+            shared_primary = True
+            rays_traced, node_traced, tri_traced = rays / frames, node_tests / frames, tri_tests / frames
         # algorithmic work of the rays the timed traversal launches actually trace (32 B and 12
         # lane-instructions per box test, 36 B and 45 per triangle test, counted in the reference's traversal order)
         alg_instr = (12.0 * node_traced + 45.0 * tri_traced) / world

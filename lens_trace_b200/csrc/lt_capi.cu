@@ -530,10 +530,16 @@ static int render_common(lt_ctx* ctx, lt_scene* scene, const LtLaunch& L, float*
     bool bigScene = scene->dev.nodeCount > 100000;
     wavefront = (L.flags & (LT_FLAG_WAVEFRONT | LT_FLAG_CULL)) ||
                 (pixels * L.frames >= minPaths && (isGI || bigScene) && L.kernel != 5);
+    if (wavefront && pixels > (1ll << 25)) {  // a queue entry carries its path id in 25 bits: one frame must fit
+      if (L.flags & (LT_FLAG_WAVEFRONT | LT_FLAG_CULL))
+        return fail(ctx, LT_ERR_UNSUPPORTED, "lt_render: the wavefront pipeline handles at most 2^25 pixels per frame");
+      wavefront = false;
+    }
     if (wavefront) {
       long long cap = maxPaths;
       long long memCap = (long long)(ctx->totalMem / 8) / 200;  // at most 1/8 of the device for the workspace
       if (cap > memCap) cap = memCap;
+      if (cap > (1ll << 25)) cap = 1ll << 25;  // a queue entry carries its path id in 25 bits
       batchFrames = (int)(cap / pixels);
       if (batchFrames < 1) batchFrames = 1;
       if (batchFrames > L.frames) batchFrames = L.frames;

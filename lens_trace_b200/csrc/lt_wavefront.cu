@@ -19,12 +19,14 @@
 #define WF_CHUNK 256  // queue entries a warp claims per global atomic
 
 struct LtWfBuffers {
-  float4* st;         // 64-byte record per path (two full sectors): [0] nrm.xyz, extW  [1] diffuse.rgb, bits(hitPrim)
-                      //                                             [2] direct.rgb, bits(depth | stage << 8)  [3] indirect.rgb, -
+  float4* st;         // 64-byte record per path, two 32-byte sectors that are read and written independently:
+                      //   S0 = [0] nrm.xyz, -  [1] diffuse.rgb, -      (written when a surface hit is shaded)
+                      //   S1 = [2] direct.rgb, extW  [3] indirect.rgb, -   (written when a shadow result is shaded)
+                      // stage and depth travel in the queue entry's path word, hitPrim is the ray's ignore index
   float4* frameCol;   // running frame colour of the path (the 25-sample blend, or the single sample)
   float4* rayO[2];    // origin.xyz, tStart
   float4* rayD[2];    // direction.xyz, bits((ignore + 1) | anyHit << 31)
-  int* rayPath[2];    // path id of the queue entry
+  int* rayPath[2];    // path id of the queue entry | stage << 25 | depth << 27  (WF_PATH_* below)
   float4* hits;       // t, u, v, bits(prim | hit << 31), indexed like the current queue
   int* counts;        // [0],[1] queue sizes (front region), [2] trace work counter, [3],[4] sizes of the back
                       // region of each queue: rays that need the select-chain slab test (a zero direction
@@ -32,6 +34,11 @@ struct LtWfBuffers {
                       // and not with the ordinary rays
   int capacity;       // entries per queue
 };
+
+#define WF_PATH_BITS 25  // a batch holds at most 2^25 paths (lt_capi.cu caps it)
+__device__ __forceinline__ int wf_pack_path(int path, int stage, int depth) {
+  return path | (stage << WF_PATH_BITS) | (depth << (WF_PATH_BITS + 2));
+}
 
 __device__ __forceinline__ void pixel_of_path(long long path, int pixels, int width, int& px, int& py, int& frameLocal) {
   frameLocal = (int)(path / pixels);
@@ -120,7 +127,7 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_primary(LtSceneDev sc, LtLaunch
     bool emit = false;
     Trav t;
     float tStart = 0.0f;
-    int ignore = -1;
+    int ignore = -1, packed = 0;
     bool anyHit = false;
     if (p < nPaths) {
       int px, py, fl;
@@ -161,16 +168,14 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_primary(LtSceneDev sc, LtLaunch
         blend_sample(pc, sample, col, fc);
         B.frameCol[p] = make_float4(fc[0], fc[1], fc[2], 0.0f);
       } else {
-        emit = true;
+        emit = true;  // a surface hit: the shadow ray of the direct light sample (direct = indirect = 0 so far)
         float4* wr = B.st + 4ll * p;
-        wr[0] = make_float4(ps.nrm[0], ps.nrm[1], ps.nrm[2], ps.extW);
-        wr[1] = make_float4(ps.diffuse[0], ps.diffuse[1], ps.diffuse[2], __int_as_float(ps.hitPrim));
-        wr[2] = make_float4(ps.direct[0], ps.direct[1], ps.direct[2],
-                            __int_as_float((ps.depth & 0xff) | (ps.stage << 8)));
-        wr[3] = make_float4(ps.indirect[0], ps.indirect[1], ps.indirect[2], 0.0f);
+        wr[0] = make_float4(ps.nrm[0], ps.nrm[1], ps.nrm[2], 0.0f);
+        wr[1] = make_float4(ps.diffuse[0], ps.diffuse[1], ps.diffuse[2], 0.0f);
+        packed = wf_pack_path((int)p, ps.stage, ps.depth);
       }
     }
-    queue_append(B, 0, emit, t.r, tStart, ignore, anyHit, (int)p, lane);
+    queue_append(B, 0, emit, t.r, tStart, ignore, anyHit, packed, lane);
   }
   if (STATS) flush_counters(gcnt, cnt);
 }
@@ -282,7 +287,8 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_shade(LtSceneDev sc, LtLaunch L
     int ignore = -1, path = 0;
     bool anyHit = false;
     if (valid) {
-      path = B.rayPath[q][i];
+      const int word = B.rayPath[q][i];
+      path = word & ((1 << WF_PATH_BITS) - 1);
       float4 o = B.rayO[q][i], d = B.rayD[q][i], hv = B.hits[i];
       r.ox = o.x; r.oy = o.y; r.oz = o.z;
       r.dx = d.x; r.dy = d.y; r.dz = d.z;
@@ -292,14 +298,32 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_shade(LtSceneDev sc, LtLaunch L
       h.prim = (int)(hb & 0x7fffffffu);
       h.hit = (int)(hb >> 31);
       PathState ps;
+      ps.stage = (word >> WF_PATH_BITS) & 3;
+      ps.depth = (int)((unsigned)word >> (WF_PATH_BITS + 2));
+      // every ray after the primary one ignores the primitive its path stands on (basic_lighting.cl:271,
+      // global_illumination.cl:294,311,350)
+      ps.hitPrim = (int)((unsigned)__float_as_int(d.w) & 0x7fffffffu) - 1;
+      // Only the half of the record this step reads is loaded:
+      //   shadow result   : nrm, diffuse (S0); the accumulators (S1) unless it is the direct sample, where they are 0
+      //   extension result: nothing for a surface hit; S0 + S1 for a light hit; S1 for a miss (final colour)
+      const bool shadowStage = ps.stage == ST_SHADOW_DIRECT || ps.stage == ST_SHADOW_EXT;
+      const bool lightHit = ps.stage == ST_EXTENSION && is_light(sc, h.prim);
+      const bool surfaceHit = ps.stage == ST_EXTENSION && !lightHit && h.hit == 1;
+      const bool needS0 = shadowStage || lightHit;
+      const bool needS1 = ps.stage == ST_SHADOW_EXT || (ps.stage == ST_EXTENSION && !surfaceHit);
       const float4* rec = B.st + 4ll * path;
-      float4 a = rec[0], b = rec[1], c = rec[2], dd = rec[3];
-      ps.nrm[0] = a.x; ps.nrm[1] = a.y; ps.nrm[2] = a.z; ps.extW = a.w;
-      ps.diffuse[0] = b.x; ps.diffuse[1] = b.y; ps.diffuse[2] = b.z; ps.hitPrim = __float_as_int(b.w);
-      ps.direct[0] = c.x; ps.direct[1] = c.y; ps.direct[2] = c.z;
-      int packed = __float_as_int(c.w);
-      ps.depth = packed & 0xff;
-      ps.stage = (packed >> 8) & 0xff;
+      float4 a = make_float4(0.0f, 0.0f, 0.0f, 0.0f), b = a, c = a, dd = a;
+      if (needS0) {
+        a = rec[0];
+        b = rec[1];
+      }
+      if (needS1) {
+        c = rec[2];
+        dd = rec[3];
+      }
+      ps.nrm[0] = a.x; ps.nrm[1] = a.y; ps.nrm[2] = a.z;
+      ps.diffuse[0] = b.x; ps.diffuse[1] = b.y; ps.diffuse[2] = b.z;
+      ps.direct[0] = c.x; ps.direct[1] = c.y; ps.direct[2] = c.z; ps.extW = c.w;
       ps.indirect[0] = dd.x; ps.indirect[1] = dd.y; ps.indirect[2] = dd.z;
       int px, py, fl;
       pixel_of_path(path, pixels, L.width, px, py, fl);
@@ -317,11 +341,14 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_shade(LtSceneDev sc, LtLaunch L
       } else {
         emit = true;
         float4* wr = B.st + 4ll * path;
-        wr[0] = make_float4(ps.nrm[0], ps.nrm[1], ps.nrm[2], ps.extW);
-        wr[1] = make_float4(ps.diffuse[0], ps.diffuse[1], ps.diffuse[2], __int_as_float(ps.hitPrim));
-        wr[2] = make_float4(ps.direct[0], ps.direct[1], ps.direct[2],
-                            __int_as_float((ps.depth & 0xff) | (ps.stage << 8)));
-        wr[3] = make_float4(ps.indirect[0], ps.indirect[1], ps.indirect[2], 0.0f);
+        if (surfaceHit) {  // new shading point
+          wr[0] = make_float4(ps.nrm[0], ps.nrm[1], ps.nrm[2], 0.0f);
+          wr[1] = make_float4(ps.diffuse[0], ps.diffuse[1], ps.diffuse[2], 0.0f);
+        } else {  // shadow result or light hit: accumulators, w of the new extension direction
+          wr[2] = make_float4(ps.direct[0], ps.direct[1], ps.direct[2], ps.extW);
+          wr[3] = make_float4(ps.indirect[0], ps.indirect[1], ps.indirect[2], 0.0f);
+        }
+        path = wf_pack_path(path, ps.stage, ps.depth);
       }
     }
     queue_append(B, 1 - q, emit, r, tStart, ignore, anyHit, path, lane);
