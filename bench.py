@@ -463,9 +463,9 @@ def main():
             if tr:
                 roof["traffic"] = tr["bytes"]
                 roof["traffic_source"] = tr["capture"]
-        pipeline = "wavefront (k_wf_primary + (k_wf_trace, k_wf_shade) x rounds + k_wf_accumulate)" \
+        pipeline = "wavefront (k_wf_primary_trace once, then per batch k_wf_primary + (k_wf_trace, k_wf_shade) x rounds + k_wf_accumulate; two batches in flight on two streams)" \
             if launches_per_step > 1 else ("k_path" if kernel >= 3 else "k_flat")
-        roof.update({"kernel": "k_wf_primary + k_wf_trace (traversal kernels of the wavefront pipeline)"
+        roof.update({"kernel": "k_wf_primary_trace + k_wf_trace (traversal kernels of the wavefront pipeline)"
                      if launches_per_step > 1 else pipeline,
                      "pipeline": pipeline,
                      "timing": "traversal launches timed live with CUDA events, kernels in isolation (LT_FLAG_SERIAL: "

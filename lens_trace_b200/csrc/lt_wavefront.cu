@@ -270,7 +270,9 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_trace(LtSceneDev sc, LtLaunch L
 }
 
 // one thread per finished ray of queue q: shade, then append the path's next ray to queue 1-q
-__global__ void __launch_bounds__(WF_BLOCK) k_wf_shade(LtSceneDev sc, LtLaunch L, LtWfBuffers B, int q, int pixels,
+// MINB: resident blocks per SM the register allocation is sized for (the kernel is bound by memory latency)
+template <int MINB>
+__global__ void __launch_bounds__(WF_BLOCK, MINB) k_wf_shade(LtSceneDev sc, LtLaunch L, LtWfBuffers B, int q, int pixels,
                                                        int frame0, int sample) {
   const PathConsts pc = path_consts(L);
   const int nFront = B.counts[q];
@@ -468,6 +470,9 @@ int lt_launch_render_wavefront(const LtSceneDev& scIn, const LtLaunch& L, float*
     if (blocksPerSm > cap) blocksPerSm = cap;
   }
   const int persistentBlocks = smCount * blocksPerSm;
+  // measured: 8 (<= 64 registers) beats 10 and 12 -- the kernel waits on dependent loads, and registers buy it
+  // more loads in flight per thread than extra warps do
+  const int shadeBlocks = lt_env_int("LT_WF_SHADE_BLOCKS_PER_SM", 8);
   const size_t wsBytes = lt_wf_workspace_bytes_padded((long long)batchFrames * pixels);
   int preLaunches = 0;
   // primary hits once per pixel per launch (exact, uncounted pipelines); kept behind the batch workspaces
@@ -513,7 +518,11 @@ int lt_launch_render_wavefront(const LtSceneDev& scIn, const LtLaunch& L, float*
           k_wf_trace<false, true><<<persistentBlocks, WF_BLOCK, smemTrace, st>>>(sc, Lq, B, q, nullptr);
         } else k_wf_trace<false, false><<<persistentBlocks, WF_BLOCK, smem, st>>>(sc, Lb, B, q, nullptr);
         mark(1, st);
-        k_wf_shade<<<grid, WF_BLOCK, 0, st>>>(sc, Lb, B, q, pixels, 0, s);
+        switch (shadeBlocks) {
+          case 12: k_wf_shade<12><<<grid, WF_BLOCK, 0, st>>>(sc, Lb, B, q, pixels, 0, s); break;
+          case 10: k_wf_shade<10><<<grid, WF_BLOCK, 0, st>>>(sc, Lb, B, q, pixels, 0, s); break;
+          default: k_wf_shade<8><<<grid, WF_BLOCK, 0, st>>>(sc, Lb, B, q, pixels, 0, s); break;
+        }
         k_wf_swap<<<1, 1, 0, st>>>(B, q);
         launches += 3;
         q = 1 - q;

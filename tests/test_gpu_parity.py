@@ -2,6 +2,8 @@
 buffers.  Bar: bit-exact for primitive ids / hit flags, and bit-exact FP32 for every deterministic
 pass (tolerance only where the fp64 device sin/cos of the hash RNG may differ from libm in the last
 place: at most a handful of pixels, each checked to 1e-4 relative)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -195,6 +197,41 @@ def test_stats_mode_does_not_change_the_image(ctx):
     a = ctx.render(sc, cam, capi.make_params(L.KERNEL_GI, 80, 60, max_ray_depth=4))
     b = ctx.render(sc, cam, capi.make_params(L.KERNEL_GI, 80, 60, max_ray_depth=4, flags=L.FLAG_STATS))
     util.assert_bit_equal(a, b)
+
+
+@pytest.mark.parametrize("kernel,depth,frames", [(L.KERNEL_GI, 4, 7), (L.KERNEL_ACCUMULATOR, 0, 6), (L.KERNEL_GI25, 2, 2)])
+def test_overlapped_batches_equal_one_stream(ctx, kernel, depth, frames):
+    """Consecutive batches of the wavefront pipeline run on two streams (a trace kernel beside the other batch's
+    shade kernel); the frame combiner is still applied in frame order, so the image is the one-stream image."""
+    sb, sc = gpu_scene(ctx, "cornell_box")
+    cam = util.default_camera(0.0, 0)
+    w, h = (160, 120) if kernel != L.KERNEL_GI25 else (64, 48)
+    imgs = []
+    for flags in (L.FLAG_WAVEFRONT, L.FLAG_WAVEFRONT | L.FLAG_SERIAL, L.FLAG_MEGAKERNEL):
+        ctx.accum_reset()
+        imgs.append(ctx.render(sc, cam, capi.make_params(kernel, w, h, max_ray_depth=depth, frames=frames,
+                                                         accum_mode=L.ACCUM_RUNNING_MEAN, flags=flags)).copy())
+    util.assert_bit_equal(imgs[0], imgs[1], "two streams vs one stream")
+    util.assert_bit_equal(imgs[0], imgs[2], "wavefront vs megakernel")
+
+
+def test_shared_primary_hits_equal_per_frame_tracing(ctx):
+    """The wavefront pipeline traces the camera ray of a pixel once per launch and starts every frame's path from
+    that record (the ray is the same in every frame); LT_WF_SHARED_PRIMARY=0 traces it per frame as the
+    reference does."""
+    sb, sc = gpu_scene(ctx, "cornell_box_lens")
+    cam = util.default_camera(0.01, 2)
+    p = capi.make_params(L.KERNEL_GI, 200, 150, max_ray_depth=3, frames=5, accum_mode=L.ACCUM_RUNNING_MEAN,
+                         flags=L.FLAG_WAVEFRONT)
+    ctx.accum_reset()
+    shared = ctx.render(sc, cam, p).copy()
+    os.environ["LT_WF_SHARED_PRIMARY"] = "0"
+    try:
+        ctx.accum_reset()
+        per_frame = ctx.render(sc, cam, p).copy()
+    finally:
+        os.environ.pop("LT_WF_SHARED_PRIMARY")
+    util.assert_bit_equal(shared, per_frame, "shared vs per-frame primary hits")
 
 
 def test_leaf_fifo_capacity_on_a_deep_tree(ctx, tmp_path):
