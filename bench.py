@@ -277,9 +277,9 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # keep stdout to the one JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # keep stdout to the one JSON line: NCCL writes its version banner (and anything else it logs) to stdout
+        # unless it is given a file -- send it to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     model, kernel, w, h, frames, depth, desc = WORKLOADS[args.workload]
