@@ -167,6 +167,13 @@ int lt_last_stats(const lt_ctx* ctx, lt_stats* out_stats);
 int lt_debug_random(lt_ctx* ctx, const float* fx, const float* fy, const float* seed, int n, float* out);
 int lt_debug_hemisphere(lt_ctx* ctx, const float* u1, const float* u2, const float* up3, int n, float* out4);
 
+/* Host-only (no device needed): the threaded form of a reference node array that lt_scene_upload builds for
+ * small trees -- 8 copies of node_count 32-byte records {lo.x lo.y lo.z hi.x | hi.y hi.z link skip}, copy o in
+ * the order the reference's traversal (basic.cu:156-196) visits the nodes for rays whose direction signs are
+ * the bits of o (LtThreadNode, include/lens_trace_b200_device.cuh).  out_records: 8 * node_count * 32 bytes.
+ * Exposed so that the layout can be checked against the reference traversal on a machine without a GPU. */
+int lt_debug_build_threaded(const void* nodes, uint64_t node_bytes, void* out_records);
+
 /* --- plug-in kernels: a user-written .cu file with the reference's kernel ABI (extern "C" __global__
  * linearKernel / tileKernel(LinearBVHNode*, Primitive*, Material*, LightContainer*, Camera*, float* out,
  * int width, int height, int depth), resources/kernels/cuda/basic.cu:331-340).  Replaces the NVRTC compile

@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "liblt_b200.so")
 SYMBOLS = [
     "lt_api_version", "lt_ctx_create", "lt_ctx_destroy", "lt_last_error", "lt_ctx_set_stream", "lt_scene_upload",
     "lt_scene_release", "lt_render", "lt_render_device", "lt_accum_reset", "lt_accum_read", "lt_primary_hits",
-    "lt_last_stats", "lt_kernel_from_path", "lt_kernel_name", "lt_debug_random", "lt_debug_hemisphere", "lt_plugin_load", "lt_render_plugin", "lt_primary_hits_flags", "lt_scene_build_lbvh", "lt_scene_download", "lt_scene_info",
+    "lt_last_stats", "lt_kernel_from_path", "lt_kernel_name", "lt_debug_random", "lt_debug_hemisphere", "lt_debug_build_threaded", "lt_plugin_load", "lt_render_plugin", "lt_primary_hits_flags", "lt_scene_build_lbvh", "lt_scene_download", "lt_scene_info",
 ]
 
 
@@ -78,6 +78,7 @@ def load():
     lib.lt_last_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
     lib.lt_debug_random.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     lib.lt_debug_hemisphere.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    lib.lt_debug_build_threaded.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
     lib.lt_plugin_load.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_int)]
     lib.lt_render_plugin.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_int, C.c_int, C.c_void_p]
@@ -238,3 +239,17 @@ class Scene:
         if self.h and self.ctx.h:
             self.ctx.lib.lt_scene_release(self.ctx.h, self.h)
         self.h = None
+
+
+THREAD_NODE = np.dtype([("lo", "<f4", 3), ("hix", "<f4"), ("hiy", "<f4"), ("hiz", "<f4"), ("link", "<i4"), ("skip", "<i4")])
+
+
+def build_threaded(nodes):
+    """Host-only: the 8 x N threaded records lt_scene_upload builds for small trees (lt_debug_build_threaded)."""
+    lib = load()
+    nodes = np.ascontiguousarray(nodes)
+    out = np.zeros((8, len(nodes)), THREAD_NODE)
+    rc = lib.lt_debug_build_threaded(nodes.ctypes.data, nodes.nbytes, out.ctypes.data)
+    if rc != 0:
+        raise LtError("lt_debug_build_threaded failed (%d): %s" % (rc, lib.lt_last_error(None).decode()))
+    return out

@@ -231,6 +231,19 @@ static void build_threaded(const RefNode* nodes, int n, std::vector<LtThreadNode
   }
 }
 
+extern "C" int lt_debug_build_threaded(const void* nodes, uint64_t node_bytes, void* out_records) {
+  if (!nodes || !out_records || node_bytes == 0 || node_bytes % sizeof(RefNode) || node_bytes / sizeof(RefNode) > 0x0fffffffull)
+    return fail(nullptr, LT_ERR_INVALID, "lt_debug_build_threaded: bad arguments");
+  int n = (int)(node_bytes / sizeof(RefNode)), depth = 0;
+  std::string why;
+  if (validate_tree((const RefNode*)nodes, n, 0x7fffffff, &depth, &why) != 0)
+    return fail(nullptr, LT_ERR_INVALID, "lt_debug_build_threaded: " + why);
+  std::vector<LtThreadNode> out;
+  build_threaded((const RefNode*)nodes, n, out);
+  memcpy(out_records, out.data(), out.size() * sizeof(LtThreadNode));
+  return LT_OK;
+}
+
 // Re-flatten on the device (inner-node ranks -> 64-byte child-pair nodes, 48-byte triangles) and fill the
 // device-side scene descriptor.  ev0 must already be recorded on the stream; on failure the scene is released.
 static int finish_scene(lt_ctx* ctx, lt_scene* s, int nNodes, int nPrims, int nMats, const RefNode& root,

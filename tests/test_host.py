@@ -169,3 +169,98 @@ def test_reference_sources_compile_against_these_headers(tmp_path):
                       (ref + "/src/main.cpp", ["-DCUDA_ENABLED", "-DOPENCL_ENABLED"])):
         r = subprocess.run(["/usr/bin/g++", "-fsyntax-only", "-I", inc] + defs + [src], capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
+
+
+def _slab(lo, hi, o, inv):
+    """intersectBounds (basic.cu:136-154) on dirIsNeg-selected bounds, FP32, NaN semantics of the select chain"""
+    f = np.float32
+    with np.errstate(all="ignore"):
+        tmin, tmax = f(f(lo[0] - o[0]) * inv[0]), f(f(hi[0] - o[0]) * inv[0])
+        tymin, tymax = f(f(lo[1] - o[1]) * inv[1]), f(f(hi[1] - o[1]) * inv[1])
+        if tmin > tymax or tymin > tmax:
+            return False
+        if tymin > tmin:
+            tmin = tymin
+        if tymax < tmax:
+            tmax = tymax
+        tzmin, tzmax = f(f(lo[2] - o[2]) * inv[2]), f(f(hi[2] - o[2]) * inv[2])
+        if tmin > tzmax or tzmin > tmax:
+            return False
+        if tzmax < tmax:
+            tmax = tzmax
+        return bool(tmax > 0)
+
+
+def test_threaded_tree_is_the_reference_traversal_order(tmp_path):
+    """lt_scene_upload's stackless layout (8 octant copies in visit order, host-built, no GPU needed): walking it
+    with `i = hit && inner ? i + 1 : skip` tests the same boxes in the same order and reaches the same leaves in
+    the same order as the reference's stack traversal (basic.cu:156-196), for rays of every sign octant
+    including axis-parallel ones (+0 / -0 direction components)."""
+    from lens_trace_b200 import capi
+    p = str(tmp_path / "synth.obj")
+    host.write_synthetic_scene(p, 10, 0x5EED)
+    scenes = [host.load_scene_buffers(p), util.scene("cornell_box"), util.scene("cornell_box_lens"),
+              util.single_triangle_scene(), util.multi_prim_leaf_scene()]
+    rng = np.random.default_rng(7)
+    f = np.float32
+    for sb in scenes:
+        nodes = sb.nodes
+        n = len(nodes)
+        T = capi.build_threaded(nodes)
+        assert T.shape == (8, n)
+        for o in range(8):  # every copy is a permutation of the nodes, bounds swapped per the octant's signs
+            want = sorted((tuple(nd["min"]), tuple(nd["max"])) for nd in nodes)
+            got = []
+            for r in T[o]:
+                lo, hi = list(r["lo"]), [r["hix"], r["hiy"], r["hiz"]]
+                mn = [hi[k] if (o >> k) & 1 else lo[k] for k in range(3)]
+                mx = [lo[k] if (o >> k) & 1 else hi[k] for k in range(3)]
+                got.append((tuple(f(v) for v in mn), tuple(f(v) for v in mx)))
+            assert sorted(got) == want
+        for trial in range(40):
+            o3 = f(rng.uniform(-6, 6, 3)) + f([0, 2.5, 0])
+            d3 = f(rng.normal(size=3))
+            if trial % 5 == 0:
+                d3[rng.integers(3)] = f(0.0) if trial % 10 == 0 else f(-0.0)
+            with np.errstate(all="ignore"):
+                inv = f(1.0) / d3
+            neg = [bool(inv[k] < 0) for k in range(3)]
+            # reference order: stack traversal on the DFS array
+            ref_boxes, ref_leaves, stack, cur = [], [], [], 0
+            while True:
+                nd = nodes[cur]
+                lo = [nd["max"][k] if neg[k] else nd["min"][k] for k in range(3)]
+                hi = [nd["min"][k] if neg[k] else nd["max"][k] for k in range(3)]
+                hit = _slab(lo, hi, o3, inv)
+                ref_boxes.append((tuple(nd["min"]), tuple(nd["max"]), hit))
+                if hit and nd["count"] > 0:
+                    ref_leaves.append(int(nd["offset"]))
+                if hit and nd["count"] == 0:
+                    if neg[nd["axis"]]:
+                        stack.append(cur + 1)
+                        cur = int(nd["offset"])
+                    else:
+                        stack.append(int(nd["offset"]))
+                        cur = cur + 1
+                else:
+                    if not stack:
+                        break
+                    cur = stack.pop()
+            # threaded order
+            o = sum(1 << k for k in range(3) if neg[k])
+            flat = T.reshape(-1)
+            thr_boxes, thr_leaves, i = [], [], o * n
+            while i != -2147483648:
+                r = flat[i]
+                lo, hi = list(r["lo"]), [r["hix"], r["hiy"], r["hiz"]]
+                hit = _slab(lo, hi, o3, inv)
+                mn = tuple(hi[k] if neg[k] else lo[k] for k in range(3))
+                mx = tuple(lo[k] if neg[k] else hi[k] for k in range(3))
+                thr_boxes.append((mn, mx, hit))
+                if hit and r["link"] < 0:
+                    thr_leaves.append(int(~r["link"]))
+                i = i + 1 if (hit and r["link"] >= 0) else int(r["skip"])
+                assert i == -2147483648 or o * n <= i < (o + 1) * n
+            assert thr_leaves == ref_leaves
+            assert [(tuple(map(float, a)), tuple(map(float, b)), h) for a, b, h in thr_boxes] == \
+                   [(tuple(map(float, a)), tuple(map(float, b)), h) for a, b, h in ref_boxes]

@@ -59,7 +59,7 @@ def main():
             print("      overlap, trace blocks/SM %d: %.2f ms" % (blocks, t), flush=True)
         os.environ.pop("LT_WF_OVERLAP_TRACE_BLOCKS_PER_SM")
         if sweep and model == "cornell_box" and kernel == L.KERNEL_GI:
-            for steps, tris, blocks in itertools.product((8, 12, 16, 24, 32), (2, 3, 4), (8, 10, 12, 16)):
+            for steps, tris, blocks in itertools.product((8, 12, 16, 24), (2, 3, 4, 6), (6, 8, 12)):
                 os.environ["LT_THREADED_NODE_STEPS"] = str(steps)
                 os.environ["LT_THREADED_TRI_TESTS"] = str(tris)
                 os.environ["LT_THREADED_BLOCKS_PER_SM"] = str(blocks)
