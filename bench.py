@@ -134,21 +134,44 @@ def cpu_oracle_rate(sb, kernel, w, h, depth, frame_list, threads=0):
     return rays / t / 1e6, rays, t, (threads if threads > 0 else cores)
 
 
+def cpu_reference_text_seconds(sb, kernel, w, h, depth, frame_list):
+    """Seconds the reference's OWN kernel file takes on the host cores for `frame_list` full frames: its OpenCL C
+    text compiled for the CPU through oracle/cl_shim (oracle/_ref/libltref_cl.so, built where /root/reference
+    exists and shipped with the repo snapshot) -- the stand-in for the north star's "OpenCL backend on a CPU
+    device (POCL)", which cannot be installed here.  None when the library is absent or the kernel has no .cl file."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import lt_ref_cl as R
+    if not R.available() or not (1 <= kernel <= 6):
+        return None
+    t = 0.0
+    for f in frame_list:
+        cam = L.make_camera(0, 2.5, -50, 0.0, f)
+        t0 = time.perf_counter()
+        R.render(kernel, sb, cam, w, h, max_ray_depth=depth if depth else 16, threads=0)
+        t += time.perf_counter() - t0
+    return t
+
+
 def run_reference(args, rank, world):
-    """--impl reference: the CPU port of the reference kernel, all host cores, bounded sample per step."""
+    """--impl reference: the reference's kernel on the CPU, all host cores, bounded sample per step.  The reference's
+    own kernel text (oracle/_ref/libltref_cl.so) when it is present, else the CPU port (oracle/lt_oracle.c); the ray
+    count of a frame always comes from the port's counters."""
     if rank != 0:
         return
     model, kernel, w, h, frames, depth, desc = WORKLOADS[args.workload]
     sb = load_scene(model)
     per_step = max(1, min(frames, 2))
     cpu_oracle_rate(sb, kernel, w, h, depth, [0])  # warm-up (page in, build)
+    use_text = cpu_reference_text_seconds(sb, kernel, w, h, depth, [0]) is not None
     for i in range(max(0, args.warmup - 1)):
         cpu_oracle_rate(sb, kernel, w, h, depth, [i])
-    rays, secs, cores = 0, 0.0, 1
+    rays, secs, port_secs, cores = 0, 0.0, 0.0, 1
     for s in range(args.steps):
-        _, r, t, cores = cpu_oracle_rate(sb, kernel, w, h, depth, [s * per_step + k for k in range(per_step)])
+        fl = [s * per_step + k for k in range(per_step)]
+        _, r, t, cores = cpu_oracle_rate(sb, kernel, w, h, depth, fl)
         rays += r
-        secs += t
+        port_secs += t
+        secs += cpu_reference_text_seconds(sb, kernel, w, h, depth, fl) if use_text else t
     value = rays / secs / 1e6
     sample = "%d of the %d frames per step at full %dx%d (frameCount = step*%d + k)" % (per_step, frames, w, h, per_step)
     line = {
@@ -157,7 +180,11 @@ def run_reference(args, rank, world):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "description": desc, "width": w, "height": h, "frames_per_step": frames,
                    "max_ray_depth": depth, "note": "ms_per_step extrapolated from the bounded sample to the whole step"},
-        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": "reference" if use_text else "port",
+                         "sample": sample, "port_value": rays / port_secs / 1e6,
+                         "what": "the reference's own kernel file compiled for the CPU (oracle/cl_shim), std::thread over "
+                                 "image rows; port_value = the C restatement (oracle/lt_oracle.c)" if use_text else
+                                 "C restatement of the reference kernel (oracle/lt_oracle.c), pthreads over image rows"},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -514,6 +541,17 @@ def main():
             line["cpu_baseline"] = {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "port",
                                     "sample": "frames 0..%d of the %d at full %dx%d (%.1f s of CPU work)" % (
                                         per - 1, frames, w, h, secs)}
+            # the reference's own kernel text on the same cores, on a smaller sample of the same frames
+            per_text = max(1, per // 2)
+            tsecs = cpu_reference_text_seconds(sb, kernel, w, h, depth, list(range(per_text)))
+            if tsecs is not None:
+                _, r_text, _, _ = cpu_oracle_rate(sb, kernel, w, h, depth, list(range(per_text))) if per_text != per else (0, r, 0, 0)
+                line["cpu_baseline"] = {
+                    "value": r_text / tsecs / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "reference",
+                    "sample": "frames 0..%d of the %d at full %dx%d (%.1f s of CPU work)" % (per_text - 1, frames, w, h, tsecs),
+                    "what": "the reference's own kernel file (OpenCL C) compiled for the CPU through oracle/cl_shim, "
+                            "std::thread over image rows -- stand-in for the OpenCL backend on a POCL CPU device",
+                    "port_value": v, "port_sample": "frames 0..%d (%.1f s), C restatement oracle/lt_oracle.c" % (per - 1, secs)}
         if world == 1 and not args.no_cull:
             # OPT-IN culled traversal (LT_FLAG_CULL): reported beside the headline, never instead of it.
             # It does less work than the reference's traversal; identity of the full-size output is checked here.
