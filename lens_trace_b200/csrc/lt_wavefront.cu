@@ -270,10 +270,14 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_trace(LtSceneDev sc, LtLaunch L
 }
 
 // one thread per finished ray of queue q: shade, then append the path's next ray to queue 1-q
-// MINB: resident blocks per SM the register allocation is sized for (the kernel is bound by memory latency)
-template <int MINB>
-__global__ void __launch_bounds__(WF_BLOCK, MINB) k_wf_shade(LtSceneDev sc, LtLaunch L, LtWfBuffers B, int q, int pixels,
-                                                       int frame0, int sample) {
+// Q (the queue consumed; 1 - Q is appended to) is a template parameter so that B.rayO[Q] etc. are static indexes:
+// with a run-time index the compiler copies the pointer arrays of the by-value struct to local memory and every
+// queue access starts with a dependent LDL.  Registers sized for 8 resident blocks (<= 64): measured against 10 and
+// 12 -- the kernel waits on dependent loads, and registers buy it more loads in flight per thread than warps do.
+template <int Q>
+__global__ void __launch_bounds__(WF_BLOCK, 8) k_wf_shade(LtSceneDev sc, LtLaunch L, LtWfBuffers B, int pixels,
+                                                          int frame0, int sample) {
+  constexpr int q = Q;
   const PathConsts pc = path_consts(L);
   const int nFront = B.counts[q];
   const int n = nFront + B.counts[3 + q];
@@ -470,9 +474,6 @@ int lt_launch_render_wavefront(const LtSceneDev& scIn, const LtLaunch& L, float*
     if (blocksPerSm > cap) blocksPerSm = cap;
   }
   const int persistentBlocks = smCount * blocksPerSm;
-  // measured: 8 (<= 64 registers) beats 10 and 12 -- the kernel waits on dependent loads, and registers buy it
-  // more loads in flight per thread than extra warps do
-  const int shadeBlocks = lt_env_int("LT_WF_SHADE_BLOCKS_PER_SM", 8);
   const size_t wsBytes = lt_wf_workspace_bytes_padded((long long)batchFrames * pixels);
   int preLaunches = 0;
   // primary hits once per pixel per launch (exact, uncounted pipelines); kept behind the batch workspaces
@@ -518,11 +519,8 @@ int lt_launch_render_wavefront(const LtSceneDev& scIn, const LtLaunch& L, float*
           k_wf_trace<false, true><<<persistentBlocks, WF_BLOCK, smemTrace, st>>>(sc, Lq, B, q, nullptr);
         } else k_wf_trace<false, false><<<persistentBlocks, WF_BLOCK, smem, st>>>(sc, Lb, B, q, nullptr);
         mark(1, st);
-        switch (shadeBlocks) {
-          case 12: k_wf_shade<12><<<grid, WF_BLOCK, 0, st>>>(sc, Lb, B, q, pixels, 0, s); break;
-          case 10: k_wf_shade<10><<<grid, WF_BLOCK, 0, st>>>(sc, Lb, B, q, pixels, 0, s); break;
-          default: k_wf_shade<8><<<grid, WF_BLOCK, 0, st>>>(sc, Lb, B, q, pixels, 0, s); break;
-        }
+        if (q == 0) k_wf_shade<0><<<grid, WF_BLOCK, 0, st>>>(sc, Lb, B, pixels, 0, s);
+        else k_wf_shade<1><<<grid, WF_BLOCK, 0, st>>>(sc, Lb, B, pixels, 0, s);
         k_wf_swap<<<1, 1, 0, st>>>(B, q);
         launches += 3;
         q = 1 - q;
