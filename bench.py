@@ -305,7 +305,9 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # keep stdout to the one JSON line: NCCL writes its version banner (and anything else it logs) to stdout
-        # unless it is given a file -- send it to stderr
+        # unless it is given a file, and it honours NCCL_DEBUG_FILE only above the VERSION level
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
