@@ -234,6 +234,29 @@ def test_shared_primary_hits_equal_per_frame_tracing(ctx):
     util.assert_bit_equal(shared, per_frame, "shared vs per-frame primary hits")
 
 
+def test_device_rng_matches_the_oracle(ctx):
+    """random() (basic_lighting.cl:64-67) on the device -- exact fmod, the CUDA library's fp64 sin -- against the
+    restatement (libm): 400 000 draws over the film positions and seeds a 1080p 64-spp step uses.  The two sines
+    may differ in the last place of the double, which flips the FP32 rounding of sin * 43758.5453 with probability
+    ~1e-9 per draw: at most 2 of the draws may differ, by one FP32 step of that product.  (A purpose-built sin for
+    |y| < pi -- 20 instructions instead of ~150 -- was measured and did not shorten the shade kernel, which waits on
+    memory, so the library function stays.)"""
+    rng = np.random.default_rng(11)
+    n = 400000
+    px = rng.integers(0, 1920, n)
+    py = rng.integers(0, 1080, n)
+    fx = (px.astype(np.float32) / np.float32(1920) + np.float32(-0.5)).astype(np.float32)
+    fy = (py.astype(np.float32) / np.float32(1080) + np.float32(-0.5)).astype(np.float32)
+    seed = rng.integers(0, 64 * 32 + 40, n).astype(np.float32)
+    seed[::97] = rng.integers(0, 1 << 24, len(seed[::97])).astype(np.float32)  # large frame counts
+    dev = ctx.debug_random(fx, fy, seed)
+    host = np.array([O.random(float(a), float(b), float(c)) for a, b, c in zip(fx, fy, seed)], dtype=np.float32)
+    bad = dev != host
+    assert bad.sum() <= 2, (int(bad.sum()), dev[bad][:4], host[bad][:4])
+    assert np.abs(dev[bad] - host[bad]).max(initial=0.0) <= 2.0 ** -8 + 1e-7
+    assert dev.min() >= 0.0 and dev.max() <= 1.0
+
+
 def test_leaf_fifo_capacity_on_a_deep_tree(ctx, tmp_path):
     """Regression: one step of the stack traversal can record three leaves (near, far, and one popped behind
     them); with room for only two the FIFO overwrote its oldest entry -- one pixel of this 1080p frame.  All
