@@ -28,10 +28,10 @@ struct LtWfBuffers {
   float4* rayD[2];    // direction.xyz, bits((ignore + 1) | anyHit << 31)
   int* rayPath[2];    // path id of the queue entry | stage << 25 | depth << 27  (WF_PATH_* below)
   float4* hits;       // t, u, v, bits(prim | hit << 31), indexed like the current queue
-  int* counts;        // [0],[1] queue sizes (front region), [2] trace work counter, [3],[4] sizes of the back
-                      // region of each queue: rays that need the select-chain slab test (a zero direction
-                      // component) are appended from the END of the queue, so they share warps with each other
-                      // and not with the ordinary rays
+  int* counts;        // [2q], [2q+1] sizes of the front and the back region of queue q (one 64-bit word per queue, so
+                      // that one atomic reserves both), [4] trace work counter.  Rays that need the select-chain
+                      // slab test (a zero direction component) are appended from the END of the queue, so they
+                      // share warps with each other and not with the ordinary rays
   int capacity;       // entries per queue
 };
 
@@ -57,26 +57,59 @@ __device__ __forceinline__ bool ray_is_degenerate(const Ray& r) {
   return !(finite3(FRCP(r.dx), FRCP(r.dy), FRCP(r.dz)) && finite3(r.ox, r.oy, r.oz));
 }
 
-// warp-aggregated append of this lane's ray (if emit) to queue `dst`
+// Block-aggregated append of this thread's ray (if emit) to queue `dst`; every thread of the block calls it the
+// same number of times.  One global atomic per block and call -- on a packed 64-bit counter (front count in the
+// low word, back count in the high word) -- instead of up to two per warp: ncu attributed 31 % of the shade
+// kernel's stall samples to the wait for those same-address atomics.
 __device__ __forceinline__ void queue_append(const LtWfBuffers& B, int dst, bool emit, const Ray& r, float tStart,
                                              int ignore, bool anyHit, int path, unsigned lane) {
+  __shared__ unsigned s_warpCount[WF_BLOCK / 32];  // front | back << 16 of each warp
+  __shared__ unsigned long long s_base;
+  const unsigned warp = threadIdx.x >> 5;
   bool back = emit && ray_is_degenerate(r);
   bool front = emit && !back;
   unsigned fm = __ballot_sync(0xffffffffu, front), bm = __ballot_sync(0xffffffffu, back);
-  int slot = -1;
-  if (fm != 0u) {
-    int base = 0, leader = __ffs(fm) - 1;
-    if ((int)lane == leader) base = atomicAdd(&B.counts[dst], __popc(fm));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (front) slot = base + __popc(fm & ((1u << lane) - 1u));
+  if (lane == 0u) s_warpCount[warp] = (unsigned)__popc(fm) | ((unsigned)__popc(bm) << 16);
+  __syncthreads();
+  unsigned before = 0u, total = 0u;
+#pragma unroll
+  for (unsigned w = 0; w < WF_BLOCK / 32; w++) {
+    unsigned c = s_warpCount[w];
+    total += c;
+    if (w < warp) before += c;
   }
-  if (bm != 0u) {
-    int base = 0, leader = __ffs(bm) - 1;
-    if ((int)lane == leader) base = atomicAdd(&B.counts[3 + dst], __popc(bm));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (back) slot = B.capacity - 1 - (base + __popc(bm & ((1u << lane) - 1u)));
+  if (threadIdx.x == 0 && total != 0u)
+    s_base = atomicAdd(reinterpret_cast<unsigned long long*>(B.counts) + dst,
+                       (unsigned long long)(total & 0xffffu) | ((unsigned long long)(total >> 16) << 32));
+  __syncthreads();
+  if (emit) {
+    const unsigned long long base = s_base;
+    int slot;
+    if (front) slot = (int)(unsigned)base + (int)(before & 0xffffu) + __popc(fm & ((1u << lane) - 1u));
+    else slot = B.capacity - 1 - ((int)(unsigned)(base >> 32) + (int)(before >> 16) + __popc(bm & ((1u << lane) - 1u)));
+    B.rayO[dst][slot] = make_float4(r.ox, r.oy, r.oz, tStart);
+    B.rayD[dst][slot] = make_float4(r.dx, r.dy, r.dz,
+                                    __int_as_float((int)((unsigned)(ignore + 1) | (anyHit ? 0x80000000u : 0u))));
+    B.rayPath[dst][slot] = path;
   }
-  if (slot >= 0) {
+}
+
+// warp-aggregated form (no block barrier) for the primary round, where most warps of a sparse view emit nothing
+__device__ __forceinline__ void queue_append_warp(const LtWfBuffers& B, int dst, bool emit, const Ray& r, float tStart,
+                                                  int ignore, bool anyHit, int path, unsigned lane) {
+  bool back = emit && ray_is_degenerate(r);
+  bool front = emit && !back;
+  unsigned fm = __ballot_sync(0xffffffffu, front), bm = __ballot_sync(0xffffffffu, back);
+  if ((fm | bm) == 0u) return;
+  unsigned long long base = 0ull;
+  if (lane == 0u)
+    base = atomicAdd(reinterpret_cast<unsigned long long*>(B.counts) + dst,
+                     (unsigned long long)__popc(fm) | ((unsigned long long)__popc(bm) << 32));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (emit) {
+    int slot;
+    if (front) slot = (int)(unsigned)base + __popc(fm & ((1u << lane) - 1u));
+    else slot = B.capacity - 1 - ((int)(unsigned)(base >> 32) + __popc(bm & ((1u << lane) - 1u)));
     B.rayO[dst][slot] = make_float4(r.ox, r.oy, r.oz, tStart);
     B.rayD[dst][slot] = make_float4(r.dx, r.dy, r.dz,
                                     __int_as_float((int)((unsigned)(ignore + 1) | (anyHit ? 0x80000000u : 0u))));
@@ -175,14 +208,14 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_primary(LtSceneDev sc, LtLaunch
         packed = wf_pack_path((int)p, ps.stage, ps.depth);
       }
     }
-    queue_append(B, 0, emit, t.r, tStart, ignore, anyHit, packed, lane);
+    queue_append_warp(B, 0, emit, t.r, tStart, ignore, anyHit, packed, lane);
   }
   if (STATS) flush_counters(gcnt, cnt);
 }
 
 // zero the queue counters before a batch
 __global__ void k_wf_reset(LtWfBuffers B) {
-  for (int k = 0; k < 5; k++) B.counts[k] = 0;
+  for (int k = 0; k < 6; k++) B.counts[k] = 0;
 }
 
 // persistent trace: lanes pull queue entries through one warp-aggregated atomic per refill
@@ -196,8 +229,8 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_trace(LtSceneDev sc, LtLaunch L
   int* list = smemStack + (THREADED ? 0 : lt_stack_levels(sc) * LT_BLOCK) + threadIdx.x;
   float* tstk = reinterpret_cast<float*>(smemStack + (lt_stack_levels(sc) + LT_MAX_BATCH) * LT_BLOCK) + threadIdx.x;
   const bool cull = !THREADED && (L.flags & 2) != 0;  // LT_FLAG_CULL: closest-hit rays skip subtrees behind the current hit
-  const int nFront = B.counts[q];
-  const int n = nFront + B.counts[3 + q];  // virtual entries: front region, then the back region
+  const int nFront = B.counts[2 * q];
+  const int n = nFront + B.counts[2 * q + 1];  // virtual entries: front region, then the back region
   const float epsThr = lt_eps(L.kernel);
   const unsigned lane = threadIdx.x & 31u;
   const unsigned stkAddr = (unsigned)__cvta_generic_to_shared(stk);
@@ -218,7 +251,7 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_trace(LtSceneDev sc, LtLaunch L
     if (need != 0u && !exhausted) {
       if (chunkNext >= chunkEnd) {
         int base = 0;
-        if (lane == 0u) base = atomicAdd(&B.counts[2], WF_CHUNK);
+        if (lane == 0u) base = atomicAdd(&B.counts[4], WF_CHUNK);
         base = __shfl_sync(0xffffffffu, base, 0);
         chunkNext = base;
         chunkEnd = min(base + WF_CHUNK, n);
@@ -279,8 +312,8 @@ __global__ void __launch_bounds__(WF_BLOCK, 8) k_wf_shade(LtSceneDev sc, LtLaunc
                                                           int frame0, int sample) {
   constexpr int q = Q;
   const PathConsts pc = path_consts(L);
-  const int nFront = B.counts[q];
-  const int n = nFront + B.counts[3 + q];
+  const int nFront = B.counts[2 * q];
+  const int n = nFront + B.counts[2 * q + 1];
   const unsigned lane = threadIdx.x & 31u;
   const int rounds = (n + (int)(gridDim.x * blockDim.x) - 1) / (int)(gridDim.x * blockDim.x);
   for (int it = 0; it < rounds; it++) {
@@ -363,9 +396,9 @@ __global__ void __launch_bounds__(WF_BLOCK, 8) k_wf_shade(LtSceneDev sc, LtLaunc
 
 // between rounds: the consumed queue becomes the next output queue
 __global__ void k_wf_swap(LtWfBuffers B, int q) {
-  B.counts[q] = 0;
-  B.counts[3 + q] = 0;
-  B.counts[2] = 0;
+  B.counts[2 * q] = 0;
+  B.counts[2 * q + 1] = 0;
+  B.counts[4] = 0;
 }
 
 // frames of the batch, in order, through the frame combiner (accumulator.frag:10-19)
