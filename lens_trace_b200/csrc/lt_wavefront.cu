@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_trace(LtSceneDev sc, LtLaunch L
   while (true) {
     bool has = entry >= 0;
     unsigned need = __ballot_sync(0xffffffffu, !has);
-    if (need != 0u && !exhausted) {
+    if (__popc(need) >= L.refillThreshold && !exhausted) {
       if (chunkNext >= chunkEnd) {
         int base = 0;
         if (lane == 0u) base = atomicAdd(&B.counts[4], WF_CHUNK);
@@ -493,6 +493,9 @@ int lt_launch_render_wavefront(const LtSceneDev& scIn, const LtLaunch& L, float*
   const bool threaded = sc.tnodes != nullptr;
   const size_t smemTrace = threaded ? (size_t)LT_MAX_BATCH * LT_BLOCK * sizeof(int) : smem;
   LtLaunch Lt = L;  // iteration shape of the trace kernel: single-box steps when threaded
+  // idle lanes a warp waits for before it fetches new rays: lanes that start together walk the top of the tree
+  // together and share its cache lines (measured: 8 is ~1 % faster than 1 on both the 83-node and the 2 M-node tree)
+  Lt.refillThreshold = lt_env_int("LT_WF_REFILL_LANES", 8);
   if (threaded) {
     blocksPerSm = lt_env_int("LT_THREADED_BLOCKS_PER_SM", 8);
     Lt.iterNodeSteps = lt_env_int("LT_THREADED_NODE_STEPS", 2 * L.iterNodeSteps);
@@ -544,13 +547,13 @@ int lt_launch_render_wavefront(const LtSceneDev& scIn, const LtLaunch& L, float*
       int q = 0;
       for (int r = 1; r < rounds; r++) {
         mark(0, st);
-        if (stats) k_wf_trace<true, false><<<persistentBlocks, WF_BLOCK, smem, st>>>(sc, Lb, B, q, dCounters);
-        else if (threaded) {
-          LtLaunch Lq = Lb;
-          Lq.iterNodeSteps = Lt.iterNodeSteps;
-          Lq.iterTriTests = Lt.iterTriTests;
-          k_wf_trace<false, true><<<persistentBlocks, WF_BLOCK, smemTrace, st>>>(sc, Lq, B, q, nullptr);
-        } else k_wf_trace<false, false><<<persistentBlocks, WF_BLOCK, smem, st>>>(sc, Lb, B, q, nullptr);
+        LtLaunch Lq = Lb;  // iteration shape of the trace kernel
+        Lq.iterNodeSteps = Lt.iterNodeSteps;
+        Lq.iterTriTests = Lt.iterTriTests;
+        Lq.refillThreshold = Lt.refillThreshold;
+        if (stats) k_wf_trace<true, false><<<persistentBlocks, WF_BLOCK, smem, st>>>(sc, Lq, B, q, dCounters);
+        else if (threaded) k_wf_trace<false, true><<<persistentBlocks, WF_BLOCK, smemTrace, st>>>(sc, Lq, B, q, nullptr);
+        else k_wf_trace<false, false><<<persistentBlocks, WF_BLOCK, smem, st>>>(sc, Lq, B, q, nullptr);
         mark(1, st);
         if (q == 0) k_wf_shade<0><<<grid, WF_BLOCK, 0, st>>>(sc, Lb, B, pixels, 0, s);
         else k_wf_shade<1><<<grid, WF_BLOCK, 0, st>>>(sc, Lb, B, pixels, 0, s);
