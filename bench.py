@@ -469,15 +469,21 @@ def main():
         trace_s = trace_ms_total / iso_steps * 1e-3
         k_s = trace_s if trace_s > 0 else kernel_ms / args.steps * 1e-3
         scene_bytes = sb.nodes.nbytes + sb.prims.nbytes
-        level = "hbm" if scene_bytes > 126e6 else ("l2" if scene_bytes > 200e3 else "l1")
+        # what the traversal kernels read: 64-byte child-pair nodes (32 B per reference node) + 48-byte triangles
+        traversal_bytes = len(sb.nodes) * 32 + len(sb.prims) * 48
+        # Level that bounds the node fetches.  A traversal set that fits the 126 MB L2 is served by L2/L1: ncu on the
+        # 1 M-triangle mesh (112 MB, profiles/r1k_*) shows DRAM at 4 % and the L1 data pipe 80 % busy, like the 21 KB
+        # Cornell tree (84 %) -- each lane of a warp gathers its own 32-byte record.  Such workloads are rated
+        # against the nominal L1 rate; only sets beyond L2 are rated against the measured HBM copy bandwidth.
+        level = "hbm" if traversal_bytes > 126e6 else "l1"
         l1_peak = sm_count * 128 * pk["sm_max_mhz"] * 1e6 / 1e9  # GB/s, nominal 128 B/clk/SM
-        bw_peak = {"hbm": pk["hbm_gbs"], "l2": None, "l1": l1_peak}[level]
+        bw_peak = {"hbm": pk["hbm_gbs"], "l1": l1_peak}[level]
         fp32 = {"achieved": alg_instr / k_s / 1e12, "peak": fp32_peak / 1e12, "unit": "T lane-instr/s",
                 "frac": alg_instr / k_s / fp32_peak}
         fetch = {"level": level, "achieved": alg_bytes / k_s / 1e9, "peak": bw_peak, "unit": "GB/s",
                  "frac": (alg_bytes / k_s / 1e9 / bw_peak) if bw_peak else None,
                  "peak_source": ("MEASURED_PEAKS.json (%s)" % pk["source"]) if level == "hbm" else
-                 ("nominal 128 B/clk/SM x SMs x sm_max_mhz" if level == "l1" else "L2 bandwidth not measured")}
+                 "nominal 128 B/clk/SM x SMs x sm_max_mhz (traversal set of %d bytes is L1/L2-resident)" % traversal_bytes}
         t_fp32 = alg_instr / fp32_peak
         t_fetch = (alg_bytes / (bw_peak * 1e9)) if bw_peak else 0.0
         if t_fetch >= t_fp32:
