@@ -541,8 +541,11 @@ static int render_common(lt_ctx* ctx, lt_scene* scene, const LtLaunch& L, float*
     // that, and for the two-ray lighting kernels on small scenes, its per-round launches and state traffic lose
     bool isGI = (L.kernel == 5 || L.kernel == 6);
     bool bigScene = scene->dev.nodeCount > 100000;
+    // second measurement (shared camera rays, overlapped batches): the two-ray lighting kernels on a small scene win
+    // too once a launch holds several batches (64 frames at 1080p: 1.31x); the 25-sample kernels stay on k_path
+    long long need = (isGI || bigScene) ? minPaths : 4 * minPaths;
     wavefront = (L.flags & (LT_FLAG_WAVEFRONT | LT_FLAG_CULL)) ||
-                (pixels * L.frames >= minPaths && (isGI || bigScene) && L.kernel != 5);
+                (pixels * L.frames >= need && L.kernel != 5 && L.kernel != 3);
     if (wavefront && pixels > (1ll << 25)) {  // a queue entry carries its path id in 25 bits: one frame must fit
       if (L.flags & (LT_FLAG_WAVEFRONT | LT_FLAG_CULL))
         return fail(ctx, LT_ERR_UNSUPPORTED, "lt_render: the wavefront pipeline handles at most 2^25 pixels per frame");
