@@ -424,8 +424,14 @@ __device__ __forceinline__ void trav_begin_threaded(Trav& t, const LtSceneDev& s
   t.iy = FRCP(t.r.dy);
   t.iz = FRCP(t.r.dz);
   t.negMask = (t.ix < 0.0f ? 1u : 0u) | (t.iy < 0.0f ? 2u : 0u) | (t.iz < 0.0f ? 4u : 0u);
-  t.cur = (int)(t.negMask & 7u) * sc.nodeCount;  // the root record of the ray's octant copy
+  const int rootRecord = (int)(t.negMask & 7u) * sc.nodeCount;  // the root record of the ray's octant copy
   if (!(finite3(t.ix, t.iy, t.iz) && finite3(t.r.ox, t.r.oy, t.r.oz))) t.negMask |= LT_EXACT_SLAB;
+  // every ray starts at the root: its box comes from the kernel parameters (constant bank) instead of a gather,
+  // and an inner root that is hit continues at its near child, the next record of the copy
+  t.cur = rootRecord;
+  if (sc.rootRef >= 0)
+    t.cur = box_test(t, sc.rootMin[0], sc.rootMax[0], sc.rootMin[1], sc.rootMax[1], sc.rootMin[2], sc.rootMax[2])
+                ? rootRecord + 1 : LT_DONE;
   t.h.t = tInit; t.h.u = 0.0f; t.h.v = 0.0f; t.h.prim = 0; t.h.hit = 0;
   t.ignore = ignore;
   t.anyHit = anyHit;
