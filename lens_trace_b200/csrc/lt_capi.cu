@@ -535,7 +535,7 @@ static int render_common(lt_ctx* ctx, lt_scene* scene, const LtLaunch& L, float*
       const char* e = getenv("LT_WAVEFRONT_MIN_PATHS");
       minPaths = e ? atoll(e) : (1ll << 23);
       e = getenv("LT_WAVEFRONT_MAX_PATHS");
-      maxPaths = e ? atoll(e) : (1ll << 25);  // paths in flight, all overlapped batches together (~200 B each)
+      maxPaths = e ? atoll(e) : (1ll << 26);  // paths in flight, all overlapped batches together (~200 B each)
     }
     // measured (tools/compare_pipelines.py): the wavefront wins once ~8M paths are in flight per batch; below
     // that, and for the two-ray lighting kernels on small scenes, its per-round launches and state traffic lose
@@ -555,7 +555,7 @@ static int render_common(lt_ctx* ctx, lt_scene* scene, const LtLaunch& L, float*
       long long cap = maxPaths;
       long long memCap = (long long)(ctx->totalMem / 8) / 200;  // at most 1/8 of the device for the workspace
       if (cap > memCap) cap = memCap;
-      if (cap > (1ll << 25)) cap = 1ll << 25;  // a queue entry carries its path id in 25 bits
+      if (cap > (1ll << 26)) cap = 1ll << 26;  // two batches; a queue entry carries its path id in 25 bits
       batchFrames = (int)(cap / pixels);
       if (batchFrames < 1) batchFrames = 1;
       if (batchFrames > L.frames) batchFrames = L.frames;
@@ -574,6 +574,11 @@ static int render_common(lt_ctx* ctx, lt_scene* scene, const LtLaunch& L, float*
         if (batchFrames >= nStreams) batchFrames = (batchFrames + nStreams - 1) / nStreams;
         else batchFrames = 1;
         ctx->wfAux.streams = nStreams;
+      }
+      {  // a queue entry carries its path id in 25 bits: at most 2^25 paths per batch
+        long long perBatch = (1ll << 25) / pixels;
+        if (perBatch < 1) perBatch = 1;
+        if (batchFrames > perBatch) batchFrames = (int)perBatch;
       }
       size_t need = lt_wf_workspace_bytes_padded((long long)batchFrames * pixels) * (size_t)nStreams +
                     lt_wf_primary_hits_bytes(pixels);
