@@ -128,31 +128,66 @@ __device__ __forceinline__ unsigned sample_index_of(const LtLaunch& L, const Pat
 // The camera ray of a pixel is the same in every frame and sample of a launch (no sub-pixel jitter anywhere in the
 // reference, basic.cu:350-358), so its hit is traced once per pixel per launch and every (pixel, frame) path of
 // every batch starts from that record: exactly the hit each of them would have found.
-__global__ void __launch_bounds__(WF_BLOCK) k_wf_primary_trace(LtSceneDev sc, LtLaunch L, float4* __restrict__ hits,
-                                                               int pixels) {
+// With `classify` (one-sample-per-frame kernels) it also sorts the pixels into three classes, because two of them
+// need no path at all: a camera ray that misses is black in every frame, one that hits a light primitive is white
+// in every frame (accumulator.cl:233-238, global_illumination.cl:257-266); only surface hits are "alive" and get
+// (pixel, frame) paths.  The alive pixels are compacted into a list (order irrelevant: paths are independent).
+struct LtWfPrimary {
+  float4* hits;        // per pixel: t, u, v, bits(prim | hit << 31)
+  int* alive;          // compacted list of alive pixels
+  unsigned char* cls;  // per pixel: 0 black, 1 white, 2 alive
+  int* aliveCount;
+};
+
+__global__ void __launch_bounds__(WF_BLOCK) k_wf_primary_trace(LtSceneDev sc, LtLaunch L, LtWfPrimary P, int pixels,
+                                                               int classify) {
   LT_SMEM_POINTERS(sc)
   (void)tstk;
-  int pixel = blockIdx.x * blockDim.x + threadIdx.x;
-  if (pixel >= pixels) return;
-  int py = pixel / L.width, px = pixel - py * L.width;
-  float fx, fy;
-  Trav t;
-  t.r = camera_ray(L.cam, px, py, L.width, L.height, fx, fy);
-  LtCounters cnt = {0, 0, 0};
-  trace<false>(t, sc, -1, lt_tinit(L.kernel), lt_eps(L.kernel), false, stk, list, cnt);
-  hits[pixel] = make_float4(t.h.t, t.h.u, t.h.v, __int_as_float((int)((unsigned)t.h.prim | (t.h.hit ? 0x80000000u : 0u))));
+  const int pixel = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = pixel < pixels;
+  bool alive = false;
+  if (valid) {
+    int py = pixel / L.width, px = pixel - py * L.width;
+    float fx, fy;
+    Trav t;
+    t.r = camera_ray(L.cam, px, py, L.width, L.height, fx, fy);
+    LtCounters cnt = {0, 0, 0};
+    trace<false>(t, sc, -1, lt_tinit(L.kernel), lt_eps(L.kernel), false, stk, list, cnt);
+    P.hits[pixel] = make_float4(t.h.t, t.h.u, t.h.v,
+                                __int_as_float((int)((unsigned)t.h.prim | (t.h.hit ? 0x80000000u : 0u))));
+    if (classify) {
+      const PathConsts pc = path_consts(L);
+      const bool lightHit = (pc.isGI || pc.whiteOnLight) && is_light(sc, t.h.prim);  // shade_step, ST_PRIMARY
+      alive = !lightHit && t.h.hit == 1;
+      P.cls[pixel] = lightHit ? 1 : (alive ? 2 : 0);
+    }
+  }
+  if (classify) {
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned m = __ballot_sync(0xffffffffu, alive);
+    if (m != 0u) {
+      int base = 0;
+      if (lane == 0u) base = atomicAdd(P.aliveCount, __popc(m));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (alive) P.alive[base + __popc(m & ((1u << lane) - 1u))] = pixel;
+    }
+  }
 }
 
 // primaryHits != nullptr: the per-pixel records of k_wf_primary_trace replace the trace (exact, uncounted launches)
+// P.alive != nullptr: only the alive pixels get paths (nf frames x aliveCount pixels, enumerated through the list);
+// the path id stays frame * pixels + pixel, so nothing downstream changes.
 template <bool STATS>
-__global__ void __launch_bounds__(WF_BLOCK) k_wf_primary(LtSceneDev sc, LtLaunch L, LtWfBuffers B, long long nPaths,
-                                                         int pixels, int sample, LtCounters* gcnt,
-                                                         const float4* __restrict__ primaryHits) {
+__global__ void __launch_bounds__(WF_BLOCK) k_wf_primary(LtSceneDev sc, LtLaunch L, LtWfBuffers B, int nf,
+                                                         int pixels, int sample, LtCounters* gcnt, LtWfPrimary P) {
   LT_SMEM_POINTERS(sc)
+  const float4* __restrict__ primaryHits = P.hits;
   const bool cull = (L.flags & 2) != 0;  // LT_FLAG_CULL: closest-hit rays skip subtrees behind the current hit
   const PathConsts pc = path_consts(L);
   const unsigned lane = threadIdx.x & 31u;
   LtCounters cnt = {0, 0, 0};
+  const int perFrame = (!STATS && P.alive != nullptr) ? *P.aliveCount : pixels;
+  const long long nPaths = (long long)nf * perFrame;
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long rounds = (nPaths + stride - 1) / stride;
   for (long long it = 0; it < rounds; it++) {
@@ -163,6 +198,11 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_primary(LtSceneDev sc, LtLaunch
     int ignore = -1, packed = 0;
     bool anyHit = false;
     if (p < nPaths) {
+      if (!STATS && P.alive != nullptr) {  // p enumerates (frame, alive pixel): turn it into the path id
+        int fl = (int)(p / perFrame);
+        int pixel = P.alive[(int)(p - (long long)fl * perFrame)];
+        p = (long long)fl * pixels + pixel;
+      }
       int px, py, fl;
       pixel_of_path(p, pixels, L.width, px, py, fl);
       float fx, fy;
@@ -403,7 +443,8 @@ __global__ void k_wf_swap(LtWfBuffers B, int q) {
 
 // frames of the batch, in order, through the frame combiner (accumulator.frag:10-19)
 __global__ void __launch_bounds__(WF_BLOCK) k_wf_accumulate(LtLaunch L, LtWfBuffers B, float* __restrict__ out,
-                                                            int pixels, int frame0, int batchFrames) {
+                                                            int pixels, int frame0, int batchFrames,
+                                                            const unsigned char* __restrict__ cls) {
   const PathConsts pc = path_consts(L);
   int pixel = blockIdx.x * blockDim.x + threadIdx.x;
   if (pixel >= pixels) return;
@@ -413,8 +454,10 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_accumulate(LtLaunch L, LtWfBuff
   else {
     sink.acc[0] = out[id + 0]; sink.acc[1] = out[id + 1]; sink.acc[2] = out[id + 2];
   }
+  const int pixelClass = cls ? cls[pixel] : 2;  // black / white pixels have no paths: their sample is constant
   for (int f = 0; f < batchFrames; f++) {
-    float4 v = B.frameCol[(long long)f * pixels + pixel];
+    float4 v = make_float4((float)pixelClass, (float)pixelClass, (float)pixelClass, 0.0f);
+    if (pixelClass == 2) v = B.frameCol[(long long)f * pixels + pixel];
     float c[3] = {v.x, v.y, v.z};
     finish_frame_colour(pc, L.kernelMode, c);
     sink.frame(L, L.cam.frameCount + (unsigned)(frame0 + f) * L.frameStride, c);
@@ -465,7 +508,8 @@ size_t lt_wf_workspace_bytes_padded(long long nPaths) {
   return lt_wf_workspace_bytes(nPaths) + 256 * 16;
 }
 
-size_t lt_wf_primary_hits_bytes(long long pixels) { return sizeof(float4) * (size_t)pixels + 256; }
+// per-launch primary records: hit (16 B), alive list entry (4 B), class (1 B) per pixel + the alive count
+size_t lt_wf_primary_hits_bytes(long long pixels) { return (sizeof(float4) + sizeof(int) + 1) * (size_t)pixels + 1024; }
 
 int lt_launch_render_wavefront(const LtSceneDev& scIn, const LtLaunch& L, float* dOut, LtCounters* dCounters,
                                void* workspace, int batchFrames, int smCount, cudaStream_t stream,
@@ -513,14 +557,23 @@ int lt_launch_render_wavefront(const LtSceneDev& scIn, const LtLaunch& L, float*
   const size_t wsBytes = lt_wf_workspace_bytes_padded((long long)batchFrames * pixels);
   int preLaunches = 0;
   // primary hits once per pixel per launch (exact, uncounted pipelines); kept behind the batch workspaces
-  float4* primaryHits = nullptr;
+  LtWfPrimary P = {nullptr, nullptr, nullptr, nullptr};
   if (!stats && !(L.flags & 2) && lt_env_int("LT_WF_SHARED_PRIMARY", 1)) {
-    primaryHits = (float4*)((char*)workspace + (size_t)nStreams * wsBytes);
+    char* pb = (char*)workspace + (size_t)nStreams * wsBytes;
+    P.hits = (float4*)pb;
+    const bool classify = samples == 1 && lt_env_int("LT_WF_ALIVE_LIST", 1);
+    if (classify) {
+      P.alive = (int*)(pb + sizeof(float4) * (size_t)pixels);
+      P.aliveCount = (int*)(pb + (sizeof(float4) + sizeof(int)) * (size_t)pixels);
+      P.cls = (unsigned char*)(P.aliveCount + 64);
+      cudaMemsetAsync(P.aliveCount, 0, sizeof(int), stream);
+    }
     mark(0, stream);
-    k_wf_primary_trace<<<(pixels + WF_BLOCK - 1) / WF_BLOCK, WF_BLOCK, smem, stream>>>(sc, L, primaryHits, pixels);
+    k_wf_primary_trace<<<(pixels + WF_BLOCK - 1) / WF_BLOCK, WF_BLOCK, smem, stream>>>(sc, L, P, pixels, classify ? 1 : 0);
     mark(1, stream);
     preLaunches = 1;
   }
+  float4* primaryHits = P.hits;
   if (overlap) {
     cudaEventRecord(aux->fork, stream);
     for (int k = 1; k < nStreams; k++) cudaStreamWaitEvent(aux->extra[k], aux->fork, 0);
@@ -540,8 +593,8 @@ int lt_launch_render_wavefront(const LtSceneDev& scIn, const LtLaunch& L, float*
       // round 0 (primary rays) fused into one kernel; its survivors are queue 0
       k_wf_reset<<<1, 1, 0, st>>>(B);
       if (!primaryHits) mark(0, st);  // a traversal kernel only when it traces the camera rays itself
-      if (stats) k_wf_primary<true><<<grid, WF_BLOCK, smem, st>>>(sc, Lb, B, nPaths, pixels, s, dCounters, nullptr);
-      else k_wf_primary<false><<<grid, WF_BLOCK, smem, st>>>(sc, Lb, B, nPaths, pixels, s, nullptr, primaryHits);
+      if (stats) k_wf_primary<true><<<grid, WF_BLOCK, smem, st>>>(sc, Lb, B, nf, pixels, s, dCounters, P);
+      else k_wf_primary<false><<<grid, WF_BLOCK, smem, st>>>(sc, Lb, B, nf, pixels, s, nullptr, P);
       if (!primaryHits) mark(1, st);
       launches += 2;
       int q = 0;
@@ -564,7 +617,7 @@ int lt_launch_render_wavefront(const LtSceneDev& scIn, const LtLaunch& L, float*
     }
     // the frame combiner is applied in frame order: this batch's accumulate follows the previous batch's
     if (overlap && batch > 0) cudaStreamWaitEvent(st, aux->order[(side + nStreams - 1) % nStreams], 0);
-    k_wf_accumulate<<<(pixels + WF_BLOCK - 1) / WF_BLOCK, WF_BLOCK, 0, st>>>(L, B, dOut, pixels, frame0, nf);
+    k_wf_accumulate<<<(pixels + WF_BLOCK - 1) / WF_BLOCK, WF_BLOCK, 0, st>>>(L, B, dOut, pixels, frame0, nf, P.cls);
     if (overlap) cudaEventRecord(aux->order[side], st);
     lastSide = side;
     launches++;

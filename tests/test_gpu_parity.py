@@ -232,6 +232,22 @@ def test_shared_primary_hits_equal_per_frame_tracing(ctx):
     finally:
         os.environ.pop("LT_WF_SHARED_PRIMARY")
     util.assert_bit_equal(shared, per_frame, "shared vs per-frame primary hits")
+    # ... and gives paths only to the pixels whose camera ray hits a surface (black / white pixels are constant)
+    os.environ["LT_WF_ALIVE_LIST"] = "0"
+    try:
+        ctx.accum_reset()
+        all_pixels = ctx.render(sc, cam, p).copy()
+    finally:
+        os.environ.pop("LT_WF_ALIVE_LIST")
+    util.assert_bit_equal(shared, all_pixels, "alive-pixel list vs paths for every pixel")
+    lit = capi.make_params(L.KERNEL_ACCUMULATOR, 200, 150, frames=5, accum_mode=L.ACCUM_RUNNING_MEAN, flags=L.FLAG_WAVEFRONT)
+    mega = capi.make_params(L.KERNEL_ACCUMULATOR, 200, 150, frames=5, accum_mode=L.ACCUM_RUNNING_MEAN, flags=L.FLAG_MEGAKERNEL)
+    ctx.accum_reset()
+    a = ctx.render(sc, cam, lit).copy()
+    ctx.accum_reset()
+    b = ctx.render(sc, cam, mega).copy()
+    util.assert_bit_equal(a, b, "accumulator kernel (white light pixels): wavefront with alive list vs megakernel")
+    assert (a == 1.0).all(axis=-1).any()  # the view contains light pixels
 
 
 def test_device_rng_matches_the_oracle(ctx):
