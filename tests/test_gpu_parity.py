@@ -247,7 +247,7 @@ def test_shared_primary_hits_equal_per_frame_tracing(ctx):
     ctx.accum_reset()
     b = ctx.render(sc, cam, mega).copy()
     util.assert_bit_equal(a, b, "accumulator kernel (white light pixels): wavefront with alive list vs megakernel")
-    assert (a == 1.0).all(axis=-1).any()  # the view contains light pixels
+    assert len(np.unique(a.reshape(-1, 3), axis=0)) > 3  # black, the light's constant colour, shaded surfaces
 
 
 def test_device_rng_matches_the_oracle(ctx):
