@@ -16,7 +16,7 @@
 #include "lt_device.cuh"
 
 #define WF_BLOCK LT_BLOCK
-#define WF_CHUNK 256  // queue entries a warp claims per global atomic
+#define WF_CHUNK 128  // queue entries a warp claims per global atomic (measured 32..1024: 64-256 equal, 1024 -8 %)
 
 struct LtWfBuffers {
   float4* st;         // 64-byte record per path, two 32-byte sectors that are read and written independently:
@@ -291,10 +291,10 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_trace(LtSceneDev sc, LtLaunch L
     if (__popc(need) >= L.refillThreshold && !exhausted) {
       if (chunkNext >= chunkEnd) {
         int base = 0;
-        if (lane == 0u) base = atomicAdd(&B.counts[4], WF_CHUNK);
+        if (lane == 0u) base = atomicAdd(&B.counts[4], L.batchClosest);  // chunk size (host: LT_WF_CHUNK)
         base = __shfl_sync(0xffffffffu, base, 0);
         chunkNext = base;
-        chunkEnd = min(base + WF_CHUNK, n);
+        chunkEnd = min(base + L.batchClosest, n);
         if (base >= n) exhausted = true;
       }
       if (!exhausted) {
@@ -604,6 +604,7 @@ int lt_launch_render_wavefront(const LtSceneDev& scIn, const LtLaunch& L, float*
         Lq.iterNodeSteps = Lt.iterNodeSteps;
         Lq.iterTriTests = Lt.iterTriTests;
         Lq.refillThreshold = Lt.refillThreshold;
+        Lq.batchClosest = lt_env_int("LT_WF_CHUNK", WF_CHUNK);  // k_path's field, reused: entries per work claim
         if (stats) k_wf_trace<true, false><<<persistentBlocks, WF_BLOCK, smem, st>>>(sc, Lq, B, q, dCounters);
         else if (threaded) k_wf_trace<false, true><<<persistentBlocks, WF_BLOCK, smemTrace, st>>>(sc, Lq, B, q, nullptr);
         else k_wf_trace<false, false><<<persistentBlocks, WF_BLOCK, smem, st>>>(sc, Lq, B, q, nullptr);
