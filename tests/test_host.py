@@ -191,6 +191,97 @@ def _slab(lo, hi, o, inv):
         return bool(tmax > 0)
 
 
+def _reference_walk(nodes, o3, inv, neg):
+    """box tests and reached leaves, in order, of the reference's stack traversal (basic.cu:156-196)"""
+    boxes, leaves, stack, cur = [], [], [], 0
+    while True:
+        nd = nodes[cur]
+        lo = [nd["max"][k] if neg[k] else nd["min"][k] for k in range(3)]
+        hi = [nd["min"][k] if neg[k] else nd["max"][k] for k in range(3)]
+        hit = _slab(lo, hi, o3, inv)
+        boxes.append((tuple(map(float, nd["min"])), tuple(map(float, nd["max"])), hit))
+        if hit and nd["count"] > 0:
+            leaves.append(int(nd["offset"]))
+        if hit and nd["count"] == 0:
+            if neg[nd["axis"]]:
+                stack.append(cur + 1)
+                cur = int(nd["offset"])
+            else:
+                stack.append(int(nd["offset"]))
+                cur = cur + 1
+        else:
+            if not stack:
+                break
+            cur = stack.pop()
+    return boxes, leaves
+
+
+def _threaded_walk(T, n, o3, inv, neg):
+    """the same, walking the stackless layout: i = hit && inner ? i + 1 : skip"""
+    o = sum(1 << k for k in range(3) if neg[k])
+    flat = T.reshape(-1)
+    boxes, leaves, i = [], [], o * n
+    while i != -2147483648:
+        r = flat[i]
+        lo, hi = list(r["lo"]), [r["hix"], r["hiy"], r["hiz"]]
+        hit = _slab(lo, hi, o3, inv)
+        mn = tuple(float(hi[k] if neg[k] else lo[k]) for k in range(3))
+        mx = tuple(float(lo[k] if neg[k] else hi[k]) for k in range(3))
+        boxes.append((mn, mx, hit))
+        if hit and r["link"] < 0:
+            leaves.append(int(~r["link"]))
+        i = i + 1 if (hit and r["link"] >= 0) else int(r["skip"])
+        assert i == -2147483648 or o * n <= i < (o + 1) * n
+    return boxes, leaves
+
+
+def _random_ray(rng, trial):
+    f = np.float32
+    o3 = f(rng.uniform(-6, 6, 3)) + f([0, 2.5, 0])
+    d3 = f(rng.normal(size=3))
+    if trial % 5 == 0:
+        d3[rng.integers(3)] = f(0.0) if trial % 10 == 0 else f(-0.0)
+    with np.errstate(all="ignore"):
+        inv = f(1.0) / d3
+    return o3, inv, [bool(inv[k] < 0) for k in range(3)]
+
+
+def test_threaded_tree_on_random_trees():
+    """Random binary trees in the reference's depth-first layout (random shapes, split axes and -- deliberately --
+    boxes that are not nested, so that every hit/miss combination occurs): the stackless walk equals the stack walk."""
+    from lens_trace_b200 import capi
+    rng = np.random.default_rng(2024)
+    for tree in range(12):
+        n_leaves = int(rng.integers(1, 40))
+        nodes = np.zeros(2 * n_leaves - 1, L.NODE)
+        counter = {"i": 0, "prim": 0}
+
+        def build(leaves):
+            i = counter["i"]
+            counter["i"] += 1
+            c = rng.uniform(-4, 4, 3) + [0, 2.5, 0]
+            h = rng.uniform(0.2, 4.0, 3)
+            nodes["min"][i] = c - h
+            nodes["max"][i] = c + h
+            if leaves == 1:
+                nodes["offset"][i] = counter["prim"]
+                nodes["count"][i] = 1 if rng.random() < 0.9 else 2
+                counter["prim"] += 1
+            else:
+                left = int(rng.integers(1, leaves))
+                nodes["axis"][i] = int(rng.integers(3))
+                build(left)
+                nodes["offset"][i] = counter["i"]
+                build(leaves - left)
+
+        build(n_leaves)
+        n = len(nodes)
+        T = capi.build_threaded(nodes)
+        for trial in range(30):
+            o3, inv, neg = _random_ray(rng, trial)
+            assert _threaded_walk(T, n, o3, inv, neg) == _reference_walk(nodes, o3, inv, neg)
+
+
 def test_threaded_tree_is_the_reference_traversal_order(tmp_path):
     """lt_scene_upload's stackless layout (8 octant copies in visit order, host-built, no GPU needed): walking it
     with `i = hit && inner ? i + 1 : skip` tests the same boxes in the same order and reaches the same leaves in
@@ -218,49 +309,5 @@ def test_threaded_tree_is_the_reference_traversal_order(tmp_path):
                 got.append((tuple(f(v) for v in mn), tuple(f(v) for v in mx)))
             assert sorted(got) == want
         for trial in range(40):
-            o3 = f(rng.uniform(-6, 6, 3)) + f([0, 2.5, 0])
-            d3 = f(rng.normal(size=3))
-            if trial % 5 == 0:
-                d3[rng.integers(3)] = f(0.0) if trial % 10 == 0 else f(-0.0)
-            with np.errstate(all="ignore"):
-                inv = f(1.0) / d3
-            neg = [bool(inv[k] < 0) for k in range(3)]
-            # reference order: stack traversal on the DFS array
-            ref_boxes, ref_leaves, stack, cur = [], [], [], 0
-            while True:
-                nd = nodes[cur]
-                lo = [nd["max"][k] if neg[k] else nd["min"][k] for k in range(3)]
-                hi = [nd["min"][k] if neg[k] else nd["max"][k] for k in range(3)]
-                hit = _slab(lo, hi, o3, inv)
-                ref_boxes.append((tuple(nd["min"]), tuple(nd["max"]), hit))
-                if hit and nd["count"] > 0:
-                    ref_leaves.append(int(nd["offset"]))
-                if hit and nd["count"] == 0:
-                    if neg[nd["axis"]]:
-                        stack.append(cur + 1)
-                        cur = int(nd["offset"])
-                    else:
-                        stack.append(int(nd["offset"]))
-                        cur = cur + 1
-                else:
-                    if not stack:
-                        break
-                    cur = stack.pop()
-            # threaded order
-            o = sum(1 << k for k in range(3) if neg[k])
-            flat = T.reshape(-1)
-            thr_boxes, thr_leaves, i = [], [], o * n
-            while i != -2147483648:
-                r = flat[i]
-                lo, hi = list(r["lo"]), [r["hix"], r["hiy"], r["hiz"]]
-                hit = _slab(lo, hi, o3, inv)
-                mn = tuple(hi[k] if neg[k] else lo[k] for k in range(3))
-                mx = tuple(lo[k] if neg[k] else hi[k] for k in range(3))
-                thr_boxes.append((mn, mx, hit))
-                if hit and r["link"] < 0:
-                    thr_leaves.append(int(~r["link"]))
-                i = i + 1 if (hit and r["link"] >= 0) else int(r["skip"])
-                assert i == -2147483648 or o * n <= i < (o + 1) * n
-            assert thr_leaves == ref_leaves
-            assert [(tuple(map(float, a)), tuple(map(float, b)), h) for a, b, h in thr_boxes] == \
-                   [(tuple(map(float, a)), tuple(map(float, b)), h) for a, b, h in ref_boxes]
+            o3, inv, neg = _random_ray(rng, trial)
+            assert _threaded_walk(T, n, o3, inv, neg) == _reference_walk(nodes, o3, inv, neg)
