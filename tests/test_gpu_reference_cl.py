@@ -45,10 +45,11 @@ def test_deterministic_kernels_vs_reference_text(ctx, name, kernel):
     assert frac_within(got, want) >= 0.998
 
 
+@pytest.mark.parametrize("name", ["cornell_box", "cornell_box_lens"])
 @pytest.mark.parametrize("kernel,depth", [(L.KERNEL_ACCUMULATOR, 16), (L.KERNEL_GI, 4), (L.KERNEL_GI, 16)])
 @pytest.mark.parametrize("mode", [0, 1])
-def test_one_stochastic_sample_vs_reference_text(ctx, kernel, depth, mode):
-    sb = util.scene("cornell_box")
+def test_one_stochastic_sample_vs_reference_text(ctx, kernel, depth, mode, name):
+    sb = util.scene(name)
     sc = ctx.upload(sb)
     for frame in (0, 3, 40):
         cam = util.default_camera(0.0, frame)
