@@ -906,15 +906,17 @@ __device__ __forceinline__ void path_reset(PathState& ps) {
 // The shading position doubles as the origin of the shadow ray and of the next extension ray, the
 // shadow ray's direction is positionToLight, and previousNormal/previousPrimitive of the reference
 // coincide with nrm/hitPrim at every point they are read -- so none of them is stored separately.
+// lightHitKnown: -1 = scan the light list here; 0 / 1 = the caller already did (is_light(sc, h.prim))
 __device__ __forceinline__ bool shade_step(const LtSceneDev& sc, const PathConsts& pc, PathState& ps, Ray& r,
                                            const Hit& h, float fx, float fy, unsigned sampleIndex, float& tStart,
-                                           int& ignore, bool& anyHit) {
+                                           int& ignore, bool& anyHit, int lightHitKnown = -1) {
   bool sampleDone = false, wantShadow = false, wantExt = false, retrace = false;
   unsigned seedBase = 0;
 
   if (ps.stage == ST_PRIMARY || ps.stage == ST_EXTENSION) {
     // basic_lighting.cl:230-246 / accumulator.cl:233-238 / global_illumination.cl:255-274, 310-331
-    bool lightHit = (ps.stage == ST_EXTENSION || pc.isGI || pc.whiteOnLight) && is_light(sc, h.prim);
+    bool lightHit = (ps.stage == ST_EXTENSION || pc.isGI || pc.whiteOnLight) &&
+                    (lightHitKnown >= 0 ? lightHitKnown != 0 : is_light(sc, h.prim));
     if (lightHit) {
       if (ps.stage == ST_PRIMARY) {
         ps.direct[0] = ps.direct[1] = ps.direct[2] = 1.0f;

@@ -47,6 +47,12 @@ __device__ __forceinline__ void pixel_of_path(long long path, int pixels, int wi
   px = pixel - py * width;
 }
 
+// frame index, pixel and film position of a path: table look-up + exact multiply-shift division when the launch
+// has them (P.film), the reference's own operations otherwise
+struct LtWfPrimary;
+__device__ __forceinline__ void film_of_path(const LtWfPrimary& P, long long path, int pixels, int width, int height,
+                                             int& frameLocal, float& fx, float& fy);
+
 // queue entry v of [0, front + back): the front region grows from slot 0, the back region from the last slot
 __device__ __forceinline__ int queue_slot(int v, int front, int capacity) {
   return v < front ? v : capacity - 1 - (v - front);
@@ -134,10 +140,28 @@ __device__ __forceinline__ unsigned sample_index_of(const LtLaunch& L, const Pat
 // (pixel, frame) paths.  The alive pixels are compacted into a list (order irrelevant: paths are independent).
 struct LtWfPrimary {
   float4* hits;        // per pixel: t, u, v, bits(prim | hit << 31)
+  float2* film;        // per pixel: the film position camera_ray computes (FP32 divisions, once per launch)
+  unsigned long long divM;  // exact division of a path id (< 2^25) by `pixels`: (id * divM) >> divS
+  int divS;                 // (Granlund & Montgomery: divS = 25 + ceil(log2 pixels), divM = ceil(2^divS / pixels))
   int* alive;          // compacted list of alive pixels
   unsigned char* cls;  // per pixel: 0 black, 1 white, 2 alive
   int* aliveCount;
 };
+
+__device__ __forceinline__ void film_of_path(const LtWfPrimary& P, long long path, int pixels, int width, int height,
+                                             int& frameLocal, float& fx, float& fy) {
+  if (P.film != nullptr) {
+    frameLocal = (int)(((unsigned long long)path * P.divM) >> P.divS);
+    float2 f = P.film[(int)(path - (long long)frameLocal * pixels)];
+    fx = f.x;
+    fy = f.y;
+  } else {
+    int px, py;
+    pixel_of_path(path, pixels, width, px, py, frameLocal);
+    fx = FADD(FDIV((float)px, (float)width), -0.5f);
+    fy = FADD(FDIV((float)py, (float)height), -0.5f);
+  }
+}
 
 __global__ void __launch_bounds__(WF_BLOCK) k_wf_primary_trace(LtSceneDev sc, LtLaunch L, LtWfPrimary P, int pixels,
                                                                int classify) {
@@ -155,6 +179,7 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_primary_trace(LtSceneDev sc, Lt
     trace<false>(t, sc, -1, lt_tinit(L.kernel), lt_eps(L.kernel), false, stk, list, cnt);
     P.hits[pixel] = make_float4(t.h.t, t.h.u, t.h.v,
                                 __int_as_float((int)((unsigned)t.h.prim | (t.h.hit ? 0x80000000u : 0u))));
+    P.film[pixel] = make_float2(fx, fy);
     if (classify) {
       const PathConsts pc = path_consts(L);
       const bool lightHit = (pc.isGI || pc.whiteOnLight) && is_light(sc, t.h.prim);  // shade_step, ST_PRIMARY
@@ -203,12 +228,10 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_primary(LtSceneDev sc, LtLaunch
         int pixel = P.alive[(int)(p - (long long)fl * perFrame)];
         p = (long long)fl * pixels + pixel;
       }
-      int px, py, fl;
-      pixel_of_path(p, pixels, L.width, px, py, fl);
+      int px = 0, py = 0, fl;
       float fx, fy;
       if (!STATS && primaryHits != nullptr) {
-        fx = FADD(FDIV((float)px, (float)L.width), -0.5f);  // the film position camera_ray computes
-        fy = FADD(FDIV((float)py, (float)L.height), -0.5f);
+        film_of_path(P, p, pixels, L.width, L.height, fl, fx, fy);  // the film position camera_ray computes
         float4 hv = primaryHits[(int)(p - (long long)fl * pixels)];
         unsigned hb = (unsigned)__float_as_int(hv.w);
         t.h.t = hv.x; t.h.u = hv.y; t.h.v = hv.z;
@@ -218,6 +241,7 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_primary(LtSceneDev sc, LtLaunch
         t.r.dx = t.r.dy = 0.0f;
         t.r.dz = 1.0f;
       } else {
+        pixel_of_path(p, pixels, L.width, px, py, fl);
         t.r = camera_ray(L.cam, px, py, L.width, L.height, fx, fy);
         if (cull) trace_cull<STATS>(t, sc, -1, pc.tInit, pc.epsThr, stk, tstk, cnt);
         else trace<STATS>(t, sc, -1, pc.tInit, pc.epsThr, false, stk, list, cnt);
@@ -349,7 +373,7 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_trace(LtSceneDev sc, LtLaunch L
 // 12 -- the kernel waits on dependent loads, and registers buy it more loads in flight per thread than warps do.
 template <int Q>
 __global__ void __launch_bounds__(WF_BLOCK, 8) k_wf_shade(LtSceneDev sc, LtLaunch L, LtWfBuffers B, int pixels,
-                                                          int frame0, int sample) {
+                                                          int frame0, int sample, LtWfPrimary P) {
   constexpr int q = Q;
   const PathConsts pc = path_consts(L);
   const int nFront = B.counts[2 * q];
@@ -404,12 +428,11 @@ __global__ void __launch_bounds__(WF_BLOCK, 8) k_wf_shade(LtSceneDev sc, LtLaunc
       ps.diffuse[0] = b.x; ps.diffuse[1] = b.y; ps.diffuse[2] = b.z;
       ps.direct[0] = c.x; ps.direct[1] = c.y; ps.direct[2] = c.z; ps.extW = c.w;
       ps.indirect[0] = dd.x; ps.indirect[1] = dd.y; ps.indirect[2] = dd.z;
-      int px, py, fl;
-      pixel_of_path(path, pixels, L.width, px, py, fl);
-      float fx = FADD(FDIV((float)px, (float)L.width), -0.5f);
-      float fy = FADD(FDIV((float)py, (float)L.height), -0.5f);
+      int fl;
+      float fx, fy;
+      film_of_path(P, path, pixels, L.width, L.height, fl, fx, fy);
       unsigned sampleIndex = sample_index_of(L, pc, frame0 + fl, sample);
-      bool done = shade_step(sc, pc, ps, r, h, fx, fy, sampleIndex, tStart, ignore, anyHit);
+      bool done = shade_step(sc, pc, ps, r, h, fx, fy, sampleIndex, tStart, ignore, anyHit, lightHit ? 1 : 0);
       if (done) {
         float col[3], fc[3];
         sample_colour(pc, ps, col);
@@ -509,7 +532,9 @@ size_t lt_wf_workspace_bytes_padded(long long nPaths) {
 }
 
 // per-launch primary records: hit (16 B), alive list entry (4 B), class (1 B) per pixel + the alive count
-size_t lt_wf_primary_hits_bytes(long long pixels) { return (sizeof(float4) + sizeof(int) + 1) * (size_t)pixels + 1024; }
+size_t lt_wf_primary_hits_bytes(long long pixels) {
+  return (sizeof(float4) + sizeof(float2) + sizeof(int) + 1) * (size_t)pixels + 1024;
+}
 
 int lt_launch_render_wavefront(const LtSceneDev& scIn, const LtLaunch& L, float* dOut, LtCounters* dCounters,
                                void* workspace, int batchFrames, int smCount, cudaStream_t stream,
@@ -557,10 +582,16 @@ int lt_launch_render_wavefront(const LtSceneDev& scIn, const LtLaunch& L, float*
   const size_t wsBytes = lt_wf_workspace_bytes_padded((long long)batchFrames * pixels);
   int preLaunches = 0;
   // primary hits once per pixel per launch (exact, uncounted pipelines); kept behind the batch workspaces
-  LtWfPrimary P = {nullptr, nullptr, nullptr, nullptr};
+  LtWfPrimary P = {};
   if (!stats && !(L.flags & 2) && lt_env_int("LT_WF_SHARED_PRIMARY", 1)) {
     char* pb = (char*)workspace + (size_t)nStreams * wsBytes;
     P.hits = (float4*)pb;
+    P.film = (float2*)(pb + sizeof(float4) * (size_t)pixels);
+    pb += sizeof(float2) * (size_t)pixels;  // the remaining arrays follow the film table
+    int l = 0;
+    while ((1ll << l) < pixels) l++;
+    P.divS = 25 + l;
+    P.divM = (unsigned long long)(((1ull << P.divS) + (unsigned long long)pixels - 1ull) / (unsigned long long)pixels);
     const bool classify = samples == 1 && lt_env_int("LT_WF_ALIVE_LIST", 1);
     if (classify) {
       P.alive = (int*)(pb + sizeof(float4) * (size_t)pixels);
@@ -609,8 +640,8 @@ int lt_launch_render_wavefront(const LtSceneDev& scIn, const LtLaunch& L, float*
         else if (threaded) k_wf_trace<false, true><<<persistentBlocks, WF_BLOCK, smemTrace, st>>>(sc, Lq, B, q, nullptr);
         else k_wf_trace<false, false><<<persistentBlocks, WF_BLOCK, smem, st>>>(sc, Lq, B, q, nullptr);
         mark(1, st);
-        if (q == 0) k_wf_shade<0><<<grid, WF_BLOCK, 0, st>>>(sc, Lb, B, pixels, 0, s);
-        else k_wf_shade<1><<<grid, WF_BLOCK, 0, st>>>(sc, Lb, B, pixels, 0, s);
+        if (q == 0) k_wf_shade<0><<<grid, WF_BLOCK, 0, st>>>(sc, Lb, B, pixels, 0, s, P);
+        else k_wf_shade<1><<<grid, WF_BLOCK, 0, st>>>(sc, Lb, B, pixels, 0, s, P);
         k_wf_swap<<<1, 1, 0, st>>>(B, q);
         launches += 3;
         q = 1 - q;
