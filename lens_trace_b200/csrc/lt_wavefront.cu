@@ -287,7 +287,8 @@ __global__ void k_wf_reset(LtWfBuffers B) {
 // holds only the leaf FIFO.  Same tests in the same order, hence the same hit records.
 template <bool STATS, bool THREADED>
 __global__ void __launch_bounds__(WF_BLOCK) k_wf_trace(LtSceneDev sc, LtLaunch L, LtWfBuffers B, int q,
-                                                       LtCounters* gcnt) {
+                                                       LtCounters* gcnt, const float4* __restrict__ rayO,
+                                                       const float4* __restrict__ rayD) {
   extern __shared__ int smemStack[];
   int* stk = smemStack + threadIdx.x;
   int* list = smemStack + (THREADED ? 0 : lt_stack_levels(sc) * LT_BLOCK) + threadIdx.x;
@@ -300,8 +301,8 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_trace(LtSceneDev sc, LtLaunch L
   const unsigned stkAddr = (unsigned)__cvta_generic_to_shared(stk);
   const unsigned fifoAddr = (unsigned)__cvta_generic_to_shared(list);
   LtCounters cnt = {0, 0, 0};
-  const float4* __restrict__ rayO = B.rayO[q];
-  const float4* __restrict__ rayD = B.rayD[q];
+  // rayO / rayD = B.rayO[q] / B.rayD[q], resolved by the host: indexing the by-value struct with a run-time q would
+  // go through a local-memory copy and generic loads
   Trav t;
   t.cur = LT_DONE;
   int entry = -1;
@@ -636,9 +637,9 @@ int lt_launch_render_wavefront(const LtSceneDev& scIn, const LtLaunch& L, float*
         Lq.iterTriTests = Lt.iterTriTests;
         Lq.refillThreshold = Lt.refillThreshold;
         Lq.batchClosest = lt_env_int("LT_WF_CHUNK", WF_CHUNK);  // k_path's field, reused: entries per work claim
-        if (stats) k_wf_trace<true, false><<<persistentBlocks, WF_BLOCK, smem, st>>>(sc, Lq, B, q, dCounters);
-        else if (threaded) k_wf_trace<false, true><<<persistentBlocks, WF_BLOCK, smemTrace, st>>>(sc, Lq, B, q, nullptr);
-        else k_wf_trace<false, false><<<persistentBlocks, WF_BLOCK, smem, st>>>(sc, Lq, B, q, nullptr);
+        if (stats) k_wf_trace<true, false><<<persistentBlocks, WF_BLOCK, smem, st>>>(sc, Lq, B, q, dCounters, B.rayO[q], B.rayD[q]);
+        else if (threaded) k_wf_trace<false, true><<<persistentBlocks, WF_BLOCK, smemTrace, st>>>(sc, Lq, B, q, nullptr, B.rayO[q], B.rayD[q]);
+        else k_wf_trace<false, false><<<persistentBlocks, WF_BLOCK, smem, st>>>(sc, Lq, B, q, nullptr, B.rayO[q], B.rayD[q]);
         mark(1, st);
         if (q == 0) k_wf_shade<0><<<grid, WF_BLOCK, 0, st>>>(sc, Lb, B, pixels, 0, s, P);
         else k_wf_shade<1><<<grid, WF_BLOCK, 0, st>>>(sc, Lb, B, pixels, 0, s, P);
