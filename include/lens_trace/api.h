@@ -282,8 +282,16 @@ struct Material {
   float emission[3];
 };
 
+// Identity of Model / AccelerationStructureExplicit objects for the renderer's device-scene cache: ids are never
+// reused, and a destroyed object's id is retired so that a renderer drops the device copy it holds for it.
+namespace lt {
+uint64_t newObjectId();
+void retireObjectId(uint64_t id);
+}  // namespace lt
+
 class Model {
 private:
+  uint64_t uniqueId;  // B200 addition
   std::vector<PrimitiveInfo> primitiveInfoList;
   std::vector<Material> materialList;
 
@@ -317,6 +325,8 @@ public:
 
   tinyobj::index_t getIndex(uint32_t index);
   uint32_t getIndexCount();
+
+  uint64_t getUniqueId() const { return uniqueId; }  // B200 addition
 };
 
 // ================================================================================================
@@ -362,6 +372,7 @@ struct LightContainer {
 
 class AccelerationStructureExplicit {
 private:
+  uint64_t uniqueId;  // B200 addition
   std::vector<LinearBVHNode> linearNodes;
   std::vector<Primitive> orderedPrimitives;
   LightContainer lightContainer;
@@ -378,6 +389,8 @@ public:
 
   uint64_t getLightContainerBufferSize();
   void* getLightContainerBuffer();
+
+  uint64_t getUniqueId() const { return uniqueId; }  // B200 addition
 };
 
 // ================================================================================================
@@ -404,15 +417,21 @@ struct lt_scene;
 
 class RendererB200 {
 private:
-  struct SceneKey {
-    const void* nodes;
-    const void* prims;
-    const void* materials;
-    uint64_t nodeBytes, primBytes, materialBytes;
-    bool operator<(const SceneKey& o) const;
+  // Device copy of one (AccelerationStructureExplicit, Model) pair.  Keyed by the objects' never-reused ids -- not
+  // by buffer addresses, which a new object can inherit from a destroyed one -- and guarded by a sampled checksum
+  // of the host buffers, so that a structure edited in place is uploaded again.  At most kMaxScenes entries (least
+  // recently used goes first); entries of destroyed objects are dropped at the next render().
+  struct CachedScene {
+    uint64_t asId, modelId;
+    uint64_t checksum;
+    uint64_t lastUse;
+    lt_scene* scene;
   };
+  static const size_t kMaxScenes = 8;
   lt_ctx* ctx;
-  std::map<SceneKey, lt_scene*> sceneCache;
+  std::vector<CachedScene> sceneCache;
+  uint64_t useCounter;
+  uint64_t seenRetireGeneration;
   std::map<std::string, int> kernelCache;
   std::map<std::string, int> pluginCache;  // user .cu kernels compiled for this context
 
@@ -423,7 +442,8 @@ public:
   RendererB200& operator=(const RendererB200&) = delete;
 
   bool valid() const { return ctx != nullptr; }
-  void forgetScenes();  // call when an AccelerationStructureExplicit was rebuilt in place
+  void forgetScenes();  // drops every cached device scene
+  size_t cachedSceneCount() const { return sceneCache.size(); }
 
   void renderCommon(const std::string& kernelFilePath, KernelMode kernelMode, const uint64_t blockSize[2],
                     const uint64_t imageDimensions[3], void* pOutputBuffer, uint64_t outputBufferSize,
@@ -447,6 +467,7 @@ public:
   RendererCUDA& operator=(const RendererCUDA&) = delete;
 
   void render(void* pRenderProperties);
+  RendererB200* b200() { return impl; }  // B200 addition: the shared implementation (scene cache control, tests)
 };
 
 // ================================================================================================
@@ -468,6 +489,7 @@ public:
   RendererOpenCL& operator=(const RendererOpenCL&) = delete;
 
   void render(void* pRenderProperties);
+  RendererB200* b200() { return impl; }  // B200 addition
 };
 
 // ================================================================================================

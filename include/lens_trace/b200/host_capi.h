@@ -37,6 +37,8 @@ void lth_camera_set_rotation(void* camera, float yaw, float pitch, float roll);
 /* platform: 0 = RendererOpenCL, 1 = RendererCUDA */
 void* lth_renderer_create(int platform);
 void lth_renderer_destroy(void* renderer, int platform);
+/* device scenes the renderer currently caches (one per live AccelerationStructureExplicit/Model pair, at most 8) */
+uint64_t lth_renderer_cached_scenes(void* renderer, int platform);
 /* Builds the RenderProperties{CUDA,OpenCL} struct and calls Renderer::render.  ext may be NULL
  * (a RenderExtensionB200*).  thread_org_mode 0 = MAX_FIT, 1 = CUSTOM with (bx, by). */
 void lth_render(void* renderer, int platform, const char* kernel_file_path, int kernel_mode, int thread_org_mode,

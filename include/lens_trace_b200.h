@@ -68,6 +68,8 @@ enum lt_flags {
                                   both produce bit-identical output) */
   LT_FLAG_SERIAL = 1 << 5,     /* wavefront pipeline: one stream, one kernel at a time (default: consecutive batches
                                   overlap on two streams; identical output).  For timing kernels in isolation. */
+  LT_FLAG_NO_STREAM = 1 << 6,  /* one thread per pixel (k_flat / fixed pixels in k_path) instead of the persistent
+                                  kernels that deal pixels to idle lanes (identical output; kept for comparison) */
   LT_FLAG_NO_THREADED = 1 << 4 /* small scenes: traverse with the stack kernels instead of the stackless threaded
                                   tree (default for scenes whose 8 octant copies stay cache resident; identical
                                   output, kept selectable so tests can compare the two) */
@@ -167,6 +169,14 @@ int lt_last_stats(const lt_ctx* ctx, lt_stats* out_stats);
 int lt_debug_random(lt_ctx* ctx, const float* fx, const float* fy, const float* seed, int n, float* out);
 int lt_debug_hemisphere(lt_ctx* ctx, const float* u1, const float* u2, const float* up3, int n, float* out4);
 
+/* Measurement hook (no reference counterpart; SURVEY.md 8(d) asks for a measured ceiling of the node fetches): the
+ * rate at which the device sustains per-lane 32-byte gathers (one ld.global.nc.v8.f32 per lane, the access a
+ * traversal step makes) at pseudo-random records of a table of table_bytes.  dependent != 0: every lane chases
+ * the index it just loaded (what one ray does); ilp = independent gathers per lane and iteration (1, 2 or 4);
+ * persistent grid of blocks_per_sm x SMs blocks of 128 threads.  out_gbs = 32 B x gathers / best-of-3 time. */
+int lt_debug_gather_peak(lt_ctx* ctx, uint64_t table_bytes, int dependent, int ilp, int blocks_per_sm, int iters,
+                         double* out_gbs, double* out_ns_per_load);
+
 /* Host-only (no device needed): the threaded form of a reference node array that lt_scene_upload builds for
  * small trees -- 8 copies of node_count 32-byte records {lo.x lo.y lo.z hi.x | hi.y hi.z link skip}, copy o in
  * the order the reference's traversal (basic.cu:156-196) visits the nodes for rays whose direction signs are
@@ -184,9 +194,11 @@ int lt_plugin_load(lt_ctx* ctx, const char* kernel_file_path, int* out_plugin_id
 int lt_render_plugin(lt_ctx* ctx, lt_scene* scene, const void* camera28, int plugin_id, int kernel_mode, int width,
                      int height, int depth, int block_x, int block_y, float* host_out);
 
-/* Maps RenderProperties*::kernelFilePath to an lt_kernel by the file's base name and, when the file
- * is readable, its defining text (SAMPLE_COUNT, epsilon); returns LT_ERR_UNSUPPORTED for a file that
- * is not one of the shipped kernels. */
+/* Maps RenderProperties*::kernelFilePath to an lt_kernel by the file's CONTENT: a descriptor file of this
+ * repository (comment lines only, one reading "lt-pipeline: <tag>") or the unmodified text of one of the seven
+ * kernel files the reference ships (content hash) selects the built-in pipeline that reproduces it.  Any other
+ * file -- including an edited copy of a shipped kernel under its old name -- returns LT_ERR_UNSUPPORTED: the
+ * renderer compiles such a .cu as a plug-in (lt_plugin_load) and reports an error for a .cl. */
 int lt_kernel_from_path(const char* kernel_file_path);
 const char* lt_kernel_name(int kernel);
 

@@ -18,6 +18,7 @@ SYMBOLS = [
     "lt_api_version", "lt_ctx_create", "lt_ctx_destroy", "lt_last_error", "lt_ctx_set_stream", "lt_scene_upload",
     "lt_scene_release", "lt_render", "lt_render_device", "lt_accum_reset", "lt_accum_read", "lt_primary_hits",
     "lt_last_stats", "lt_kernel_from_path", "lt_kernel_name", "lt_debug_random", "lt_debug_hemisphere", "lt_debug_build_threaded", "lt_plugin_load", "lt_render_plugin", "lt_primary_hits_flags", "lt_scene_build_lbvh", "lt_scene_download", "lt_scene_info",
+    "lt_debug_gather_peak",
 ]
 
 
@@ -82,6 +83,8 @@ def load():
     lib.lt_plugin_load.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_int)]
     lib.lt_render_plugin.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_int, C.c_int, C.c_void_p]
+    lib.lt_debug_gather_peak.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.lt_kernel_from_path.argtypes = [C.c_char_p]
     lib.lt_kernel_name.argtypes = [C.c_int]
     lib.lt_kernel_name.restype = C.c_char_p
@@ -224,6 +227,13 @@ class Context:
         self._check(self.lib.lt_debug_hemisphere(self.h, u1.ctypes.data, u2.ctypes.data, up.ctypes.data, u1.size,
                                                  out.ctypes.data), "lt_debug_hemisphere")
         return out
+
+    def gather_peak(self, table_bytes, dependent=False, ilp=4, blocks_per_sm=8, iters=2000):
+        """(GB/s, ns per gather and lane) of per-lane 32-byte gathers on a table of table_bytes"""
+        gbs, ns = C.c_double(0.0), C.c_double(0.0)
+        self._check(self.lib.lt_debug_gather_peak(self.h, int(table_bytes), 1 if dependent else 0, ilp, blocks_per_sm,
+                                                  iters, C.byref(gbs), C.byref(ns)), "lt_debug_gather_peak")
+        return gbs.value, ns.value
 
     def stats(self):
         s = Stats()

@@ -20,6 +20,7 @@ struct lt_ctx {
   float* dOut = nullptr;  // context-owned output / accumulator
   size_t outFloats = 0;
   LtCounters* dCounters = nullptr;
+  int* dWork = nullptr;  // work counters of the persistent kernels
   std::vector<cudaEvent_t> traceEvents;  // pairs of events around traversal launches (timed when synchronous)
   std::vector<LtPlugin*> plugins;  // compiled user kernels, by id
   RefCamera* dCamera = nullptr;    // camera buffer for plug-in launches
@@ -56,6 +57,8 @@ static int fail(lt_ctx* ctx, int code, const std::string& msg) {
       return fail(ctx, LT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));             \
   } while (0)
 
+int lt_internal_ctx_device(const lt_ctx* ctx) { return ctx->device; }
+
 extern "C" int lt_api_version(void) { return LT_API_VERSION; }
 
 extern "C" const char* lt_last_error(const lt_ctx* ctx) { return ctx ? ctx->error.c_str() : g_error.c_str(); }
@@ -87,6 +90,7 @@ extern "C" int lt_ctx_create(int device_ordinal, lt_ctx** out_ctx) {
   if (e2 == cudaSuccess) e2 = cudaEventCreate(&ctx->ev0);
   if (e2 == cudaSuccess) e2 = cudaEventCreate(&ctx->ev1);
   if (e2 == cudaSuccess) e2 = cudaMalloc(&ctx->dCounters, sizeof(LtCounters));
+  if (e2 == cudaSuccess) e2 = cudaMalloc(&ctx->dWork, 256);
   for (int k = 1; k < LT_WF_MAX_STREAMS; k++)
     if (e2 == cudaSuccess) e2 = cudaStreamCreateWithFlags(&ctx->wfAux.extra[k], cudaStreamNonBlocking);
   if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&ctx->wfAux.fork, cudaEventDisableTiming);
@@ -108,6 +112,7 @@ extern "C" void lt_ctx_destroy(lt_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   if (ctx->dOut) cudaFree(ctx->dOut);
   if (ctx->dCounters) cudaFree(ctx->dCounters);
+  if (ctx->dWork) cudaFree(ctx->dWork);
   if (ctx->wfWorkspace) cudaFree(ctx->wfWorkspace);
   if (ctx->dCamera) cudaFree(ctx->dCamera);
   for (LtPlugin* p : ctx->plugins) lt_plugin_free(p);
@@ -159,6 +164,9 @@ static int validate_tree(const RefNode* nodes, int nodeCount, int primCount, int
       todo.push_back({i + 1, d + 1});
     }
   }
+  // every array entry must belong to the tree: the re-flatten kernels process all nodeCount entries and size their
+  // output from the full-binary-tree count, so an unreachable entry would be followed unvalidated
+  if (visited != nodeCount) { *why = "node array has entries that are not reachable from the root"; return -1; }
   *stackDepth = maxInner;
   return 0;
 }
@@ -546,6 +554,13 @@ static int render_common(lt_ctx* ctx, lt_scene* scene, const LtLaunch& L, float*
     long long need = (isGI || bigScene) ? minPaths : 4 * minPaths;
     wavefront = (L.flags & (LT_FLAG_WAVEFRONT | LT_FLAG_CULL)) ||
                 (pixels * L.frames >= need && L.kernel != 5 && L.kernel != 3);
+    // a queue entry carries the bounce depth in 5 bits (wf_pack_path): deeper bounce caps stay on the megakernel,
+    // which is the same arithmetic per path (0 = the reference constant 16)
+    if (wavefront && isGI && L.maxRayDepth > 32) {
+      if (L.flags & (LT_FLAG_WAVEFRONT | LT_FLAG_CULL))
+        return fail(ctx, LT_ERR_UNSUPPORTED, "lt_render: the wavefront pipeline handles max_ray_depth <= 32 (use the default schedule)");
+      wavefront = false;
+    }
     if (wavefront && pixels > (1ll << 25)) {  // a queue entry carries its path id in 25 bits: one frame must fit
       if (L.flags & (LT_FLAG_WAVEFRONT | LT_FLAG_CULL))
         return fail(ctx, LT_ERR_UNSUPPORTED, "lt_render: the wavefront pipeline handles at most 2^25 pixels per frame");
@@ -609,7 +624,8 @@ static int render_common(lt_ctx* ctx, lt_scene* scene, const LtLaunch& L, float*
                                                         batchFrames, ctx->stats.sm_count, ctx->stream,
                                                         timeTrace ? ctx->traceEvents.data() : nullptr, kMaxTracePairs,
                                                         &tracePairs, overlapBatches ? &ctx->wfAux : nullptr)
-                           : lt_launch_render(scene->dev, L, dOut, ctx->dCounters, ctx->stream);
+                           : lt_launch_render(scene->dev, L, dOut, ctx->dCounters, ctx->dWork, ctx->stats.sm_count,
+                                              ctx->stream);
   CK(cudaGetLastError());
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
   ctx->stats.kernel_launches = launches;
@@ -799,32 +815,79 @@ extern "C" const char* lt_kernel_name(int kernel) {
   return (kernel >= 0 && kernel < LT_KERNEL_COUNT) ? kKernelNames[kernel] : "unknown";
 }
 
+// kernelFilePath -> built-in pipeline, by CONTENT (the reference compiles whatever text the file holds,
+// src/cuda/renderer_cuda.cpp:20-39,52-55, so the name alone must never select a pipeline):
+//   * a descriptor file of this repository -- nothing but // comment lines, one of them "lt-pipeline: <tag>" -- or
+//   * a file whose text is, byte for byte (CR dropped), one of the seven kernel files the reference ships
+//     (lt_kernel_hashes.inc: FNV-1a-64 + length; only hashes are stored)
+// maps to the hand-written pipeline that reproduces that kernel.  Anything else -- including an EDITED copy of a
+// shipped kernel under its old name -- is a user kernel: LT_ERR_UNSUPPORTED here; the renderer then compiles a .cu
+// as a plug-in (lt_plugin_load) and reports an error for a .cl (OpenCL C cannot be compiled for sm_100a here).
+struct LtKernelHash {
+  unsigned long long hash;
+  size_t bytes;
+  int kernel;
+};
+static const LtKernelHash kShippedKernels[] = {
+#include "lt_kernel_hashes.inc"
+};
+
+static bool read_file(const char* path, std::string* text) {
+  FILE* f = fopen(path, "rb");
+  if (!f) return false;
+  char buf[4096];
+  size_t n;
+  while ((n = fread(buf, 1, sizeof buf, f)) > 0) text->append(buf, n);
+  fclose(f);
+  return true;
+}
+
 extern "C" int lt_kernel_from_path(const char* path) {
   if (!path) return LT_ERR_INVALID;
-  std::string p(path);
-  size_t slash = p.find_last_of('/');
-  std::string base = slash == std::string::npos ? p : p.substr(slash + 1);
-  if (base == "basic.cu") return LT_KERNEL_BASIC_CU;
-  if (base == "basic.cl") return LT_KERNEL_BASIC_CL;
-  if (base == "custom_opencl.cl") return LT_KERNEL_CUSTOM_BARY;
-  if (base == "basic_lighting.cl") return LT_KERNEL_LIGHTING25;
-  if (base == "accumulator.cl") return LT_KERNEL_ACCUMULATOR;
-  if (base == "global_illumination.cl") {
-    // the resources/ variant blends SAMPLE_COUNT samples per launch (global_illumination.cl:3,408-415),
-    // the example's variant takes one (examples/global_illumination/.../global_illumination.cl:407)
-    FILE* f = fopen(path, "rb");
-    if (f) {
-      std::string text;
-      char buf[4096];
-      size_t n;
-      while ((n = fread(buf, 1, sizeof buf, f)) > 0) text.append(buf, n);
-      fclose(f);
-      if (text.find("lt-pipeline: gi25") != std::string::npos) return LT_KERNEL_GI25;
-      if (text.find("lt-pipeline: gi") != std::string::npos) return LT_KERNEL_GI;
-      return text.find("SAMPLE_COUNT") != std::string::npos ? LT_KERNEL_GI25 : LT_KERNEL_GI;
-    }
-    return p.find("opencl/") != std::string::npos ? LT_KERNEL_GI25 : LT_KERNEL_GI;
+  std::string text;
+  if (!read_file(path, &text)) {
+    g_error = std::string("lt_kernel_from_path: cannot open kernel file '") + path + "'";
+    return LT_ERR_UNSUPPORTED;
   }
-  g_error = "lt_kernel_from_path: '" + p + "' is not one of the shipped kernels";
+  // descriptor: comment lines only, carrying a pipeline tag
+  static const struct { const char* tag; int kernel; } kTags[] = {
+      {"basic_cu", LT_KERNEL_BASIC_CU},     {"basic_cl", LT_KERNEL_BASIC_CL},       {"custom_bary", LT_KERNEL_CUSTOM_BARY},
+      {"lighting25", LT_KERNEL_LIGHTING25}, {"accumulator", LT_KERNEL_ACCUMULATOR}, {"gi25", LT_KERNEL_GI25},
+      {"gi", LT_KERNEL_GI}};
+  bool commentsOnly = true;
+  int tagged = -1;
+  for (size_t pos = 0; pos < text.size();) {
+    size_t end = text.find('\n', pos);
+    if (end == std::string::npos) end = text.size();
+    std::string line = text.substr(pos, end - pos);
+    pos = end + 1;
+    size_t b = line.find_first_not_of(" \t\r");
+    if (b == std::string::npos) continue;
+    if (line.compare(b, 2, "//") != 0) {
+      commentsOnly = false;
+      break;
+    }
+    size_t t = line.find("lt-pipeline:");
+    if (t != std::string::npos && tagged < 0) {
+      std::string tag = line.substr(t + 12);
+      size_t tb = tag.find_first_not_of(" \t"), te = tag.find_last_not_of(" \t\r");
+      tag = tb == std::string::npos ? "" : tag.substr(tb, te - tb + 1);
+      for (size_t k = 0; k < sizeof kTags / sizeof kTags[0]; k++)
+        if (tag == kTags[k].tag) tagged = kTags[k].kernel;
+    }
+  }
+  if (commentsOnly && tagged >= 0) return tagged;
+  // the reference's own shipped text
+  unsigned long long h = 14695981039346656037ull;
+  size_t bytes = 0;
+  for (size_t i = 0; i < text.size(); i++) {
+    if (text[i] == '\r') continue;
+    h = (h ^ (unsigned char)text[i]) * 1099511628211ull;
+    bytes++;
+  }
+  for (size_t k = 0; k < sizeof kShippedKernels / sizeof kShippedKernels[0]; k++)
+    if (kShippedKernels[k].hash == h && kShippedKernels[k].bytes == bytes) return kShippedKernels[k].kernel;
+  g_error = std::string("lt_kernel_from_path: '") + path + "' is neither a kernel descriptor nor the unmodified text of "
+            "a shipped kernel (user kernels: .cu files are compiled as plug-ins, .cl files are not supported)";
   return LT_ERR_UNSUPPORTED;
 }

@@ -635,6 +635,22 @@ __host__ __device__ inline float lt_eps(int kernel) {
 }
 
 // camera ray, basic.cu:350-358; fused forms as NVRTC+ptxas emit them (oracle/notes_fma_order.md)
+// c, s = cosf(cam.yaw), sinf(cam.yaw): the same for every pixel, so persistent kernels evaluate them once
+__device__ __forceinline__ Ray camera_ray_cs(const RefCamera& cam, float c, float s, int px, int py, int width,
+                                             int height, float& fx, float& fy) {
+  fx = FADD(FDIV((float)px, (float)width), -0.5f);
+  fy = FADD(FDIV((float)py, (float)height), -0.5f);
+  float dx0 = FSUB(0.0f, fx);
+  Ray r;
+  r.ox = FADD(fx, cam.position[0]);
+  r.oy = FADD(fy, cam.position[1]);
+  r.oz = FADD(cam.position[2], 0.0f);
+  r.dx = FFMA(dx0, c, FMUL(s, 5.0f));
+  r.dy = FSUB(0.0f, fy);
+  r.dz = FFMA(c, 5.0f, -FMUL(dx0, s));
+  return r;
+}
+
 __device__ __forceinline__ Ray camera_ray(const RefCamera& cam, int px, int py, int width, int height, float& fx,
                                           float& fy) {
   fx = FADD(FDIV((float)px, (float)width), -0.5f);
@@ -718,52 +734,68 @@ __device__ __forceinline__ void lerp_fused(const float* a, const float* b, const
   for (int k = 0; k < 3; k++) out[k] = FFMA(v, c[k], FFMA(a[k], w0, FMUL(u, b[k])));
 }
 
+// The two refraction steps of traceRayThroughLens (basic.cu:245-298) on their own, for kernels that run the lens
+// rays through a resumable traversal: each turns (ray, hit) into the next ray of the lens path and returns the
+// primitive that ray ignores.  lens_refract_in keeps the w of the refracted direction for lens_refract_out.
+__device__ __forceinline__ int lens_refract_in(const LtSceneDev& sc, Ray& r, const Hit& h, float& r2w) {
+  const RefPrim* prim = sc.prims + h.prim;
+  const RefMaterial* mat = sc.mats + prim->materialIndex;
+  float w0 = bary0(h.u, h.v);
+  float pos[3], nrm[3];
+  lerp_fused(prim->a, prim->b, prim->c, w0, h.u, h.v, pos);
+  lerp_fused(prim->na, prim->nb, prim->nc, w0, h.u, h.v, nrm);
+  float n = FRCP(mat->ior);
+  float c = dot3z(r.dx, r.dy, r.dz, nrm[0], nrm[1], nrm[2]);
+  float sinT2 = (float)__dmul_rn(__dsub_rn(1.0, (double)FMUL(c, c)), (double)FMUL(n, n));
+  float cosT = (float)__dsqrt_rn(__dsub_rn(1.0, (double)sinT2));
+  float k = FFMA(c, -n, -cosT);
+  float dx = FFMA(r.dx, n, FMUL(nrm[0], k));
+  float dy = FFMA(r.dy, n, FMUL(nrm[1], k));
+  float dz = FFMA(r.dz, n, FMUL(nrm[2], k));
+  r2w = FFMA(n, 0.0f, FMUL(k, 0.0f));
+  r.ox = pos[0]; r.oy = pos[1]; r.oz = pos[2];
+  r.dx = dx; r.dy = dy; r.dz = dz;
+  return h.prim;
+}
+
+__device__ __forceinline__ int lens_refract_out(const LtSceneDev& sc, Ray& r, const Hit& h, float r2w) {
+  const RefPrim* prim = sc.prims + h.prim;
+  const RefMaterial* mat = sc.mats + prim->materialIndex;
+  float w0 = bary0(h.u, h.v);
+  float pos[3], nrm[3];
+  lerp_fused(prim->a, prim->b, prim->c, w0, h.u, h.v, pos);
+  lerp_fused(prim->na, prim->nb, prim->nc, w0, h.u, h.v, nrm);
+  float ior = mat->ior;
+  float c2 = FFMA(0.0f, r2w, FFMA(-r.dz, nrm[2], FFMA(r.dx, -nrm[0], -FMUL(r.dy, nrm[1]))));
+  float sinT2b = (float)__dmul_rn(__dsub_rn(1.0, (double)FMUL(c2, c2)), (double)FMUL(ior, ior));
+  float cosTb = (float)__dsqrt_rn(__dsub_rn(1.0, (double)sinT2b));
+  float k2 = FFMA(c2, -ior, -cosTb);
+  float dx = FFMA(r.dx, ior, -FMUL(k2, nrm[0]));
+  float dy = FFMA(r.dy, ior, -FMUL(k2, nrm[1]));
+  float dz = FFMA(r.dz, ior, -FMUL(k2, nrm[2]));
+  r.ox = pos[0]; r.oy = pos[1]; r.oz = pos[2];
+  r.dx = dx; r.dy = dy; r.dz = dz;
+  return h.prim;
+}
+
 // traceRayThroughLens + refract, basic.cu:79-86,245-298 (operation order: oracle/notes_fma_order.md)
 // On entry t holds the primary ray and its hit; on exit the refracted ray and its hit.
 template <bool STATS>
 __device__ void lens_path(const LtSceneDev& sc, Trav& t, float tInit, float epsThr, int* stk, int* list,
                           float* tstk, bool cull, LtCounters& cnt) {
-  const RefPrim* prim = sc.prims + t.h.prim;
-  const RefMaterial* mat = sc.mats + prim->materialIndex;
-  int firstPrim = t.h.prim;
-  float w0 = bary0(t.h.u, t.h.v);
-  float pos[3], nrm[3];
-  lerp_fused(prim->a, prim->b, prim->c, w0, t.h.u, t.h.v, pos);
-  lerp_fused(prim->na, prim->nb, prim->nc, w0, t.h.u, t.h.v, nrm);
-
-  float n = FRCP(mat->ior);
-  float c = dot3z(t.r.dx, t.r.dy, t.r.dz, nrm[0], nrm[1], nrm[2]);
-  float sinT2 = (float)__dmul_rn(__dsub_rn(1.0, (double)FMUL(c, c)), (double)FMUL(n, n));
-  float cosT = (float)__dsqrt_rn(__dsub_rn(1.0, (double)sinT2));
-  float k = FFMA(c, -n, -cosT);
-  float dx = FFMA(t.r.dx, n, FMUL(nrm[0], k));
-  float dy = FFMA(t.r.dy, n, FMUL(nrm[1], k));
-  float dz = FFMA(t.r.dz, n, FMUL(nrm[2], k));
-  float r2w = FFMA(n, 0.0f, FMUL(k, 0.0f));
-  t.r.ox = pos[0]; t.r.oy = pos[1]; t.r.oz = pos[2];
-  t.r.dx = dx; t.r.dy = dy; t.r.dz = dz;
-  if (cull) trace_cull<STATS>(t, sc, firstPrim, tInit, epsThr, stk, tstk, cnt);
-  else trace<STATS>(t, sc, firstPrim, tInit, epsThr, false, stk, list, cnt);
-
-  int secondPrim = t.h.prim;
-  prim = sc.prims + secondPrim;
-  mat = sc.mats + prim->materialIndex;
-  w0 = bary0(t.h.u, t.h.v);
-  lerp_fused(prim->a, prim->b, prim->c, w0, t.h.u, t.h.v, pos);
-  lerp_fused(prim->na, prim->nb, prim->nc, w0, t.h.u, t.h.v, nrm);
-
-  float ior = mat->ior;
-  float c2 = FFMA(0.0f, r2w, FFMA(-t.r.dz, nrm[2], FFMA(t.r.dx, -nrm[0], -FMUL(t.r.dy, nrm[1]))));
-  float sinT2b = (float)__dmul_rn(__dsub_rn(1.0, (double)FMUL(c2, c2)), (double)FMUL(ior, ior));
-  float cosTb = (float)__dsqrt_rn(__dsub_rn(1.0, (double)sinT2b));
-  float k2 = FFMA(c2, -ior, -cosTb);
-  dx = FFMA(t.r.dx, ior, -FMUL(k2, nrm[0]));
-  dy = FFMA(t.r.dy, ior, -FMUL(k2, nrm[1]));
-  dz = FFMA(t.r.dz, ior, -FMUL(k2, nrm[2]));
-  t.r.ox = pos[0]; t.r.oy = pos[1]; t.r.oz = pos[2];
-  t.r.dx = dx; t.r.dy = dy; t.r.dz = dz;
-  if (cull) trace_cull<STATS>(t, sc, secondPrim, tInit, epsThr, stk, tstk, cnt);
-  else trace<STATS>(t, sc, secondPrim, tInit, epsThr, false, stk, list, cnt);
+  float r2w;
+  {
+    const Hit h = t.h;
+    const int firstPrim = lens_refract_in(sc, t.r, h, r2w);
+    if (cull) trace_cull<STATS>(t, sc, firstPrim, tInit, epsThr, stk, tstk, cnt);
+    else trace<STATS>(t, sc, firstPrim, tInit, epsThr, false, stk, list, cnt);
+  }
+  {
+    const Hit h = t.h;
+    const int secondPrim = lens_refract_out(sc, t.r, h, r2w);
+    if (cull) trace_cull<STATS>(t, sc, secondPrim, tInit, epsThr, stk, tstk, cnt);
+    else trace<STATS>(t, sc, secondPrim, tInit, epsThr, false, stk, list, cnt);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------

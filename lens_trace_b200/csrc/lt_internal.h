@@ -28,14 +28,18 @@ struct LtCounters {
   unsigned long long rays, nodeTests, triTests;
 };
 
+struct lt_ctx;
+int lt_internal_ctx_device(const lt_ctx* ctx);  // lt_capi.cu
+
 // launchers implemented in lt_kernels.cu (all asynchronous on `stream`; return launches made)
 int lt_launch_reflatten(const RefNode* dNodes, int nodeCount, const RefPrim* dPrims, int primCount,
                         const int* dInnerRank, LtWideNode* dWide, LtTri* dTris, cudaStream_t stream);
 int lt_launch_inner_flags(const RefNode* dNodes, int nodeCount, int* dFlags, cudaStream_t stream);
 size_t lt_scan_temp_bytes(int n);
 int lt_launch_exclusive_scan(void* dTemp, size_t tempBytes, const int* dIn, int* dOut, int n, cudaStream_t stream);
-int lt_launch_render(const LtSceneDev& sc, const LtLaunch& L, float* dOut, LtCounters* dCounters,
-                     cudaStream_t stream);
+// dWork: one zero-initialisable int of device memory (work counter of the persistent kernels)
+int lt_launch_render(const LtSceneDev& sc, const LtLaunch& L, float* dOut, LtCounters* dCounters, int* dWork,
+                     int smCount, cudaStream_t stream);
 int lt_launch_primary_hits(const LtSceneDev& sc, const RefCamera& cam, int kernel, int flags, int width, int height,
                            int* dIds, int* dHit, float* dTuv, cudaStream_t stream);
 int lt_launch_debug_random(const float* fx, const float* fy, const float* seed, int n, float* out, cudaStream_t stream);

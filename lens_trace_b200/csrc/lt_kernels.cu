@@ -17,6 +17,9 @@
 #include "lt_device.cuh"
 
 #include <cub/device/device_scan.cuh>
+#include <stdlib.h>
+
+#define LT_LAUNCH_FLAG_NO_STREAM 64  // == LT_FLAG_NO_STREAM (include/lens_trace_b200.h)
 
 template <bool STATS>
 __global__ void __launch_bounds__(LT_BLOCK) k_flat(LtSceneDev sc, LtLaunch L, float* __restrict__ out,
@@ -63,6 +66,124 @@ __global__ void __launch_bounds__(LT_BLOCK) k_flat(LtSceneDev sc, LtLaunch L, fl
   }
 }
 
+// Persistent form of k_flat for the exact, uncounted launches: blocks stay resident (SMs x blocks per SM), a warp
+// claims runs of pixels from a global counter -- enumerated as 8x4 tiles so that the rays a warp holds stay
+// neighbours -- and deals them to whichever lanes are idle, so no lane, warp or SM waits for the longest ray of a
+// fixed pixel tile (ncu on the 1 M-triangle mesh: with one ray per thread the SMs were active 45 % of the kernel's
+// duration, profiles/r2a_*).  Rays run through the same software-pipelined traversal as k_wf_trace; the lens path
+// (basic.cu:245-298) is two more rays of the same lane.  Same tests in the same order per ray as k_flat, hence the
+// same picture (tests compare the two through LT_FLAG_NO_STREAM).
+template <bool THREADED>
+__global__ void __launch_bounds__(LT_BLOCK) k_flat_stream(LtSceneDev sc, LtLaunch L, float* __restrict__ out,
+                                                          int* __restrict__ work) {
+  extern __shared__ int smemStack[];
+  int* stk = smemStack + threadIdx.x;
+  int* list = smemStack + (THREADED ? 0 : lt_stack_levels(sc) * LT_BLOCK) + threadIdx.x;
+  const unsigned stkAddr = (unsigned)__cvta_generic_to_shared(stk);
+  const unsigned fifoAddr = (unsigned)__cvta_generic_to_shared(list);
+  const unsigned lane = threadIdx.x & 31u;
+  const float tInit = lt_tinit(L.kernel), epsThr = lt_eps(L.kernel);
+  const float camC = cosf(L.cam.yaw), camS = sinf(L.cam.yaw);
+  const int tilesX = (L.width + 7) >> 3, tilesY = (L.height + 3) >> 2;
+  const int n = tilesX * tilesY * 32;  // entries: tile-major, 32 per 8x4 tile (entries off the image are skipped)
+  LtCounters cnt = {0, 0, 0};
+  Trav t;
+  t.cur = LT_DONE;
+  int pixel = -1;      // py * width + px of the lane's current pixel, -1 = idle
+  int stage = 0;       // 0 camera ray, 1 first lens ray, 2 second lens ray
+  int baseMat = 0;     // material of the camera ray's hit (kept when the lens path ends in a miss)
+  float r2w = 0.0f;
+  int chunkNext = 0, chunkEnd = 0;
+  bool exhausted = false;
+  while (true) {
+    bool has = pixel >= 0;
+    unsigned need = __ballot_sync(0xffffffffu, !has);
+    if (__popc(need) >= L.refillThreshold && !exhausted) {
+      if (chunkNext >= chunkEnd) {
+        int base = 0;
+        if (lane == 0u) base = atomicAdd(work, L.batchClosest);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        chunkNext = base;
+        chunkEnd = min(base + L.batchClosest, n);
+        if (base >= n) exhausted = true;
+      }
+      if (!exhausted) {
+        int idx = chunkNext + __popc(need & ((1u << lane) - 1u));
+        chunkNext += __popc(need);
+        if (!has && idx < chunkEnd) {
+          int tile = idx >> 5, l = idx & 31;
+          int ty = tile / tilesX, tx = tile - ty * tilesX;
+          int px = (tx << 3) + (l & 7), py = (ty << 2) + (l >> 3);
+          if (px < L.width && py < L.height) {
+            float fx, fy;
+            t.r = camera_ray_cs(L.cam, camC, camS, px, py, L.width, L.height, fx, fy);
+            if (THREADED) trav_begin_threaded(t, sc, -1, tInit, false);
+            else trav_begin<false>(t, sc, -1, tInit, false, cnt);
+            pixel = py * L.width + px;
+            stage = 0;
+          }
+        }
+      }
+    }
+    has = pixel >= 0;
+    if (!__any_sync(0xffffffffu, has)) {
+      if (exhausted) break;
+      continue;
+    }
+    if (has) {
+      bool finished = t.cur == LT_DONE && t.qHead == t.qTail;  // a ray that missed the root box
+      if (!finished) {
+        if (THREADED) finished = trav_iter_threaded(t, sc.tnodes, sc.tris, fifoAddr, epsThr, L.iterNodeSteps, L.iterTriTests);
+        else finished = trav_iter_lean<false>(t, sc, stkAddr, fifoAddr, epsThr, L.iterNodeSteps, L.iterTriTests, cnt);
+      }
+      if (finished) {
+        bool done = true;
+        float color[3] = {0.0f, 0.0f, 0.0f};
+        if (stage == 0) {
+          if (t.h.hit == 1) {
+            if (L.kernel == 2) {  // custom_opencl.cl:240
+              color[0] = t.h.u;
+              color[1] = t.h.v;
+              color[2] = bary0(t.h.u, t.h.v);
+            } else {  // basic.cu:312-326
+              baseMat = sc.prims[t.h.prim].materialIndex;
+              if (sc.mats[baseMat].dissolve < 1.0f) {
+                const Hit h = t.h;
+                int ignore = lens_refract_in(sc, t.r, h, r2w);
+                if (THREADED) trav_begin_threaded(t, sc, ignore, tInit, false);
+                else trav_begin<false>(t, sc, ignore, tInit, false, cnt);
+                stage = 1;
+                done = false;
+              }
+            }
+          }
+        } else if (stage == 1) {
+          const Hit h = t.h;
+          int ignore = lens_refract_out(sc, t.r, h, r2w);
+          if (THREADED) trav_begin_threaded(t, sc, ignore, tInit, false);
+          else trav_begin<false>(t, sc, ignore, tInit, false, cnt);
+          stage = 2;
+          done = false;
+        }
+        if (done) {
+          if (L.kernel != 2 && (stage != 0 || t.h.hit == 1)) {
+            const RefMaterial* mat = sc.mats + ((stage == 2 && t.h.hit == 1) ? sc.prims[t.h.prim].materialIndex : baseMat);
+            color[0] = mat->diffuse[0];
+            color[1] = mat->diffuse[1];
+            color[2] = mat->diffuse[2];
+          }
+          long long id = (long long)pixel * L.depth;
+          FrameSink sink;
+          sink.begin(L, out, id);
+          for (int f = 0; f < L.frames; f++) sink.frame(L, L.cam.frameCount + (unsigned)f * L.frameStride, color);
+          sink.end(out, id);
+          pixel = -1;
+        }
+      }
+    }
+  }
+}
+
 // One thread = one pixel, persistent over all frames and samples of the launch.  The warp alternates
 // between two phases:
 //   S (shade/regenerate): lanes whose ray has finished consume the hit and produce their next ray
@@ -73,30 +194,32 @@ __global__ void __launch_bounds__(LT_BLOCK) k_flat(LtSceneDev sc, LtLaunch L, fl
 //     for a new ray, so long rays never hold the other 31 lanes idle.  Traversal state is resumable.
 template <bool STATS>
 __global__ void __launch_bounds__(LT_BLOCK) k_path(LtSceneDev sc, LtLaunch L, float* __restrict__ out,
-                                                   LtCounters* gcnt) {
+                                                   LtCounters* gcnt, int* __restrict__ work) {
   LT_SMEM_POINTERS(sc)
   (void)tstk;  // the persistent megakernel does not cull (LT_FLAG_CULL selects the wavefront pipeline)
   const unsigned stkAddr = (unsigned)__cvta_generic_to_shared(stk);
   const unsigned fifoAddr = (unsigned)__cvta_generic_to_shared(list);
-  int px, py;
-  bool alive = thread_pixel(L.width, L.height, px, py);
+  const unsigned lane = threadIdx.x & 31u;
   LtCounters cnt = {0, 0, 0};
   const PathConsts pc = path_consts(L);
+  // work == nullptr: one thread per pixel of a 16x8 tile per block (grid = tiles).  Otherwise the blocks are
+  // persistent and a lane whose pixel has finished all its frames takes the next pixel from a global counter
+  // (8x4 tiles, like k_flat_stream): on large scenes the fixed assignment left SMs idle behind the slowest tiles.
+  const bool dynamic = work != nullptr;
+  const float camC = cosf(L.cam.yaw), camS = sinf(L.cam.yaw);
+  const int tilesX = (L.width + 7) >> 3, tilesY = (L.height + 3) >> 2;
+  const int nEntries = tilesX * tilesY * 32;
+  int chunkNext = 0, chunkEnd = 0;
+  bool exhausted = !dynamic;
 
   float fx = 0.0f, fy = 0.0f;
   Ray cameraRay = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 1.0f};
   long long id = 0;
   FrameSink sink;
   sink.acc[0] = sink.acc[1] = sink.acc[2] = 0.0f;
-  if (alive) {
-    cameraRay = camera_ray(L.cam, px, py, L.width, L.height, fx, fy);
-    id = ((long long)py * L.width + px) * L.depth;
-    sink.begin(L, out, id);
-  }
-
   int frame = 0, sample = 0;
   float frameColor[3] = {0.0f, 0.0f, 0.0f};
-  unsigned sampleIndex = (pc.samplesPerFrame == 25) ? L.cam.frameCount * 32u : L.cam.frameCount;
+  unsigned sampleIndex = 0u;
   PathState ps;
   ps.nrm[0] = ps.nrm[1] = ps.nrm[2] = 0.0f;
   ps.diffuse[0] = ps.diffuse[1] = ps.diffuse[2] = 0.0f;
@@ -108,14 +231,52 @@ __global__ void __launch_bounds__(LT_BLOCK) k_path(LtSceneDev sc, LtLaunch L, fl
   const bool threaded = !STATS && sc.tnodes != nullptr;  // small scene: stackless threaded tree, same tests
   Trav t;
   t.r = cameraRay;
-  bool traversing = false;
-  if (alive) {
-    if (threaded) trav_begin_threaded(t, sc, -1, pc.tInit, false);
-    else trav_begin<STATS>(t, sc, -1, pc.tInit, false, cnt);
-    traversing = (t.cur != LT_DONE);
-  }
+  t.cur = LT_DONE;
+  bool traversing = false, alive = false;
+  int px = 0, py = 0;
+  bool fresh = !dynamic && thread_pixel(L.width, L.height, px, py);  // this lane was just given pixel (px, py)
 
   while (true) {
+    // ---------------- phase F: idle lanes take the next pixels ----------------
+    if (dynamic && !exhausted) {
+      unsigned need = __ballot_sync(0xffffffffu, !alive);
+      if (__popc(need) >= L.batchAnyHit) {  // (field reused by the dynamic form: idle lanes that trigger a fetch)
+        if (chunkNext >= chunkEnd) {
+          int base = 0;
+          if (lane == 0u) base = atomicAdd(work, 128);
+          base = __shfl_sync(0xffffffffu, base, 0);
+          chunkNext = base;
+          chunkEnd = min(base + 128, nEntries);
+          if (base >= nEntries) exhausted = true;
+        }
+        if (!exhausted) {
+          int idx = chunkNext + __popc(need & ((1u << lane) - 1u));
+          chunkNext += __popc(need);
+          if (!alive && idx < chunkEnd) {
+            int tile = idx >> 5, l = idx & 31;
+            int ty = tile / tilesX, tx = tile - ty * tilesX;
+            px = (tx << 3) + (l & 7);
+            py = (ty << 2) + (l >> 3);
+            fresh = px < L.width && py < L.height;
+          }
+        }
+      }
+    }
+    if (fresh) {
+      fresh = false;
+      alive = true;
+      cameraRay = camera_ray_cs(L.cam, camC, camS, px, py, L.width, L.height, fx, fy);
+      id = ((long long)py * L.width + px) * L.depth;
+      sink.begin(L, out, id);
+      frame = 0;
+      sample = 0;
+      sampleIndex = (pc.samplesPerFrame == 25) ? L.cam.frameCount * 32u : L.cam.frameCount;
+      path_reset(ps);
+      t.r = cameraRay;
+      if (threaded) trav_begin_threaded(t, sc, -1, pc.tInit, false);
+      else trav_begin<STATS>(t, sc, -1, pc.tInit, false, cnt);
+      traversing = (t.cur != LT_DONE);
+    }
     // ---------------- phase S: consume finished rays, generate the next ones ----------------
     while (alive && !traversing) {
       float tStart;
@@ -150,18 +311,22 @@ __global__ void __launch_bounds__(LT_BLOCK) k_path(LtSceneDev sc, LtLaunch L, fl
       else trav_begin<STATS>(t, sc, ignore, tStart, anyHit, cnt);
       traversing = (t.cur != LT_DONE);
     }
-    if (!__any_sync(0xffffffffu, alive)) break;
+    if (!__any_sync(0xffffffffu, alive)) {
+      if (exhausted) break;
+      continue;
+    }
 
     // ---------------- phase T: resumable traversal ----------------
     while (true) {
       unsigned active = __ballot_sync(0xffffffffu, traversing);
       if (active == 0u) break;
-      bool waiting = __any_sync(0xffffffffu, alive && !traversing);
+      bool waiting = __any_sync(0xffffffffu, (alive && !traversing) || (!alive && !exhausted));
       if (waiting && __popc(active) < L.refillThreshold) break;
+      if (!exhausted && __popc(__ballot_sync(0xffffffffu, !alive)) >= L.batchAnyHit) break;
       if (traversing) {
         if (threaded) {
           traversing = !trav_iter_threaded(t, sc.tnodes, sc.tris, fifoAddr, pc.epsThr, 2 * L.iterNodeSteps, L.iterTriTests);
-        } else if (L.batchClosest > 0) {  // leaf-list form: whole batches of box tests, then the recorded triangles
+        } else if (!dynamic && L.batchClosest > 0) {  // leaf-list form: whole batches of box tests, then the recorded triangles
           int n = trav_collect<STATS>(t, sc, stk, list, t.anyHit ? L.batchAnyHit : L.batchClosest, cnt);
           trav_test<STATS>(t, sc, list, n, pc.epsThr, cnt);
           traversing = (t.cur != LT_DONE);
@@ -294,6 +459,24 @@ int lt_launch_reflatten(const RefNode* dNodes, int nodeCount, const RefPrim* dPr
 
 static size_t stack_bytes(const LtSceneDev& sc, bool cull) { return lt_traversal_smem(sc, cull); }
 
+// Dynamic shared memory beyond 48 KB needs an opt-in per kernel (and per device): the culled mode on a tree deeper
+// than 40 levels asks for up to (2 * 64 + 16) * 512 = 73 728 bytes.
+#define LT_MAX_TRAVERSAL_SMEM ((2 * 64 + LT_MAX_BATCH) * LT_BLOCK * (int)sizeof(int))
+static void opt_in_smem(size_t smem) {
+  if (smem <= 48 * 1024) return;
+  static bool done[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || done[dev]) return;
+  done[dev] = true;
+  cudaFuncSetAttribute(k_flat<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_MAX_TRAVERSAL_SMEM);
+  cudaFuncSetAttribute(k_flat<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_MAX_TRAVERSAL_SMEM);
+  cudaFuncSetAttribute(k_path<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_MAX_TRAVERSAL_SMEM);
+  cudaFuncSetAttribute(k_path<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_MAX_TRAVERSAL_SMEM);
+  cudaFuncSetAttribute(k_primary_hits, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_MAX_TRAVERSAL_SMEM);
+  cudaFuncSetAttribute(k_flat_stream<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_MAX_TRAVERSAL_SMEM);
+}
+
 static int tile_blocks(int width, int height) { return ((width + 15) / 16) * ((height + 7) / 8); }
 
 // the threaded tree is used by the exact, uncounted kernels only (the stats kernels count in the stack traversal,
@@ -304,19 +487,61 @@ static LtSceneDev scene_for_flags(const LtSceneDev& sc, int flags) {
   return s;
 }
 
-int lt_launch_render(const LtSceneDev& scIn, const LtLaunch& L, float* dOut, LtCounters* dCounters,
-                     cudaStream_t stream) {
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+int lt_launch_render(const LtSceneDev& scIn, const LtLaunch& L, float* dOut, LtCounters* dCounters, int* dWork,
+                     int smCount, cudaStream_t stream) {
   const LtSceneDev sc = scene_for_flags(scIn, L.flags);
   int blocks = tile_blocks(L.width, L.height);
   size_t smem = stack_bytes(sc, (L.flags & 2) != 0);
+  opt_in_smem(smem);
   bool stats = (L.flags & 1) != 0;
   bool flat = (L.kernel <= 2);
+  // exact, uncounted launches of the deterministic pipelines: persistent blocks with per-lane refill
+  if (flat && !(L.flags & (1 | 2 | LT_LAUNCH_FLAG_NO_STREAM)) && dWork != nullptr) {
+    const bool threaded = sc.tnodes != nullptr;
+    const size_t smemStream = threaded ? (size_t)LT_MAX_BATCH * LT_BLOCK * sizeof(int) : smem;
+    int blocksPerSm = (int)((200 * 1024) / smemStream);
+    const int cap = env_int("LT_STREAM_BLOCKS_PER_SM", 8);
+    if (blocksPerSm > cap) blocksPerSm = cap;
+    if (blocksPerSm < 1) blocksPerSm = 1;
+    int grid = smCount * blocksPerSm;
+    const int warpsNeeded = (((L.width + 7) >> 3) * ((L.height + 3) >> 2) + 3) / 4;  // blocks of 4 warps, one tile each
+    if (grid > warpsNeeded) grid = warpsNeeded;
+    LtLaunch Ls = L;
+    Ls.refillThreshold = env_int("LT_STREAM_REFILL_LANES", 8);
+    Ls.batchClosest = env_int("LT_STREAM_CHUNK", 128);  // entries per work claim
+    if (threaded) Ls.iterNodeSteps = 2 * L.iterNodeSteps;
+    cudaMemsetAsync(dWork, 0, sizeof(int), stream);
+    if (threaded) k_flat_stream<true><<<grid, LT_BLOCK, smemStream, stream>>>(sc, Ls, dOut, dWork);
+    else k_flat_stream<false><<<grid, LT_BLOCK, smemStream, stream>>>(sc, Ls, dOut, dWork);
+    return 1;
+  }
   if (flat) {
     if (stats) k_flat<true><<<blocks, LT_BLOCK, smem, stream>>>(sc, L, dOut, dCounters);
     else k_flat<false><<<blocks, LT_BLOCK, smem, stream>>>(sc, L, dOut, nullptr);
   } else {
-    if (stats) k_path<true><<<blocks, LT_BLOCK, smem, stream>>>(sc, L, dOut, dCounters);
-    else k_path<false><<<blocks, LT_BLOCK, smem, stream>>>(sc, L, dOut, nullptr);
+    // exact, uncounted launches on large scenes: persistent blocks, lanes take pixels from a global counter
+    const bool dynamicPixels = !stats && dWork != nullptr && !(L.flags & LT_LAUNCH_FLAG_NO_STREAM) &&
+                               (sc.nodeCount > env_int("LT_PATH_DYNAMIC_MIN_NODES", 100000) || env_int("LT_PATH_DYNAMIC", 0));
+    if (dynamicPixels) {
+      int blocksPerSm = (int)((200 * 1024) / smem);
+      const int cap = env_int("LT_PATH_BLOCKS_PER_SM", 5);  // 94 registers: 5 blocks of 128 threads
+      if (blocksPerSm > cap) blocksPerSm = cap;
+      if (blocksPerSm < 1) blocksPerSm = 1;
+      int grid = smCount * blocksPerSm;
+      if (grid > blocks) grid = blocks;
+      LtLaunch Ld = L;
+      Ld.batchAnyHit = env_int("LT_PATH_FETCH_LANES", 8);
+      cudaMemsetAsync(dWork, 0, sizeof(int), stream);
+      k_path<false><<<grid, LT_BLOCK, smem, stream>>>(sc, Ld, dOut, nullptr, dWork);
+      return 1;
+    }
+    if (stats) k_path<true><<<blocks, LT_BLOCK, smem, stream>>>(sc, L, dOut, dCounters, nullptr);
+    else k_path<false><<<blocks, LT_BLOCK, smem, stream>>>(sc, L, dOut, nullptr, nullptr);
   }
   return 1;
 }
@@ -324,6 +549,7 @@ int lt_launch_render(const LtSceneDev& scIn, const LtLaunch& L, float* dOut, LtC
 int lt_launch_primary_hits(const LtSceneDev& scIn, const RefCamera& cam, int kernel, int flags, int width, int height,
                            int* dIds, int* dHit, float* dTuv, cudaStream_t stream) {
   const LtSceneDev sc = scene_for_flags(scIn, flags);
+  opt_in_smem(stack_bytes(sc, (flags & 2) != 0));
   k_primary_hits<<<tile_blocks(width, height), LT_BLOCK, stack_bytes(sc, (flags & 2) != 0), stream>>>(
       sc, cam, kernel, flags, width, height, dIds, dHit, dTuv);
   return 1;

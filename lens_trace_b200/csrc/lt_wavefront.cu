@@ -528,13 +528,15 @@ static LtWfBuffers carve(void* workspace, long long nPaths) {
 }
 
 size_t lt_wf_workspace_bytes_padded(long long nPaths) {
-  // carve() rounds every array up to 256 bytes
-  return lt_wf_workspace_bytes(nPaths) + 256 * 16;
+  // carve() rounds every array up to 256 bytes; the total is a multiple of 256 as well, because batch workspace
+  // k > 0 and the primary-record block start at multiples of it and hold float4 arrays (an odd path count would
+  // otherwise leave them 8 bytes off a 16-byte boundary: misaligned float4 accesses)
+  return ((lt_wf_workspace_bytes(nPaths) + 256 * 16) + 255) & ~(size_t)255;
 }
 
 // per-launch primary records: hit (16 B), alive list entry (4 B), class (1 B) per pixel + the alive count
 size_t lt_wf_primary_hits_bytes(long long pixels) {
-  return (sizeof(float4) + sizeof(float2) + sizeof(int) + 1) * (size_t)pixels + 1024;
+  return (sizeof(float4) + sizeof(float2) + sizeof(int) + 1) * (size_t)pixels + 1024 + 5 * 256;  // 5 arrays, 256-aligned
 }
 
 int lt_launch_render_wavefront(const LtSceneDev& scIn, const LtLaunch& L, float* dOut, LtCounters* dCounters,
@@ -555,6 +557,20 @@ int lt_launch_render_wavefront(const LtSceneDev& scIn, const LtLaunch& L, float*
   const int maxDepth = L.maxRayDepth > 0 ? L.maxRayDepth : 16;
   const int rounds = isGI ? 2 + 2 * maxDepth : 2;
   const size_t smem = lt_traversal_smem(sc, (L.flags & 2) != 0);
+  if (smem > 48 * 1024) {  // beyond 48 KB (culled mode on a tree deeper than 40) dynamic shared memory is an opt-in
+    static bool done[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !done[dev]) {
+      done[dev] = true;
+      const int most = (2 * 64 + LT_MAX_BATCH) * LT_BLOCK * (int)sizeof(int);
+      cudaFuncSetAttribute(k_wf_primary_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, most);
+      cudaFuncSetAttribute(k_wf_primary<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, most);
+      cudaFuncSetAttribute(k_wf_primary<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, most);
+      cudaFuncSetAttribute(k_wf_trace<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, most);
+      cudaFuncSetAttribute(k_wf_trace<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, most);
+    }
+  }
   int blocksPerSm = (int)((200 * 1024) / smem);  // shared memory is what limits residency of the persistent kernel
   if (blocksPerSm > 8) blocksPerSm = 8;
   if (blocksPerSm < 1) blocksPerSm = 1;
@@ -585,19 +601,23 @@ int lt_launch_render_wavefront(const LtSceneDev& scIn, const LtLaunch& L, float*
   // primary hits once per pixel per launch (exact, uncounted pipelines); kept behind the batch workspaces
   LtWfPrimary P = {};
   if (!stats && !(L.flags & 2) && lt_env_int("LT_WF_SHARED_PRIMARY", 1)) {
-    char* pb = (char*)workspace + (size_t)nStreams * wsBytes;
-    P.hits = (float4*)pb;
-    P.film = (float2*)(pb + sizeof(float4) * (size_t)pixels);
-    pb += sizeof(float2) * (size_t)pixels;  // the remaining arrays follow the film table
+    char* pb = (char*)workspace + (size_t)nStreams * wsBytes;  // 256-aligned: wsBytes is a multiple of 256
+    auto take = [&](size_t bytes) {
+      char* r = pb;
+      pb += (bytes + 255) & ~(size_t)255;
+      return r;
+    };
+    P.hits = (float4*)take(sizeof(float4) * (size_t)pixels);
+    P.film = (float2*)take(sizeof(float2) * (size_t)pixels);
     int l = 0;
     while ((1ll << l) < pixels) l++;
     P.divS = 25 + l;
     P.divM = (unsigned long long)(((1ull << P.divS) + (unsigned long long)pixels - 1ull) / (unsigned long long)pixels);
     const bool classify = samples == 1 && lt_env_int("LT_WF_ALIVE_LIST", 1);
     if (classify) {
-      P.alive = (int*)(pb + sizeof(float4) * (size_t)pixels);
-      P.aliveCount = (int*)(pb + (sizeof(float4) + sizeof(int)) * (size_t)pixels);
-      P.cls = (unsigned char*)(P.aliveCount + 64);
+      P.alive = (int*)take(sizeof(int) * (size_t)pixels);
+      P.aliveCount = (int*)take(256);
+      P.cls = (unsigned char*)take((size_t)pixels);
       cudaMemsetAsync(P.aliveCount, 0, sizeof(int), stream);
     }
     mark(0, stream);

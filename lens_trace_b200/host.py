@@ -20,7 +20,7 @@ SYMBOLS = [
     "lth_as_primitive_buffer", "lth_as_primitive_bytes", "lth_as_light_buffer", "lth_as_light_bytes",
     "lth_camera_create", "lth_camera_destroy", "lth_camera_buffer", "lth_camera_set_frame_count",
     "lth_camera_increment_frame_count", "lth_camera_set_position", "lth_camera_set_rotation", "lth_renderer_create",
-    "lth_renderer_destroy", "lth_render", "lth_write_synthetic_scene", "lth_run_scene_file",
+    "lth_renderer_destroy", "lth_renderer_cached_scenes", "lth_render", "lth_write_synthetic_scene", "lth_run_scene_file",
 ]
 
 
@@ -66,6 +66,8 @@ def load():
     lib.lth_camera_set_rotation.argtypes = [vp, C.c_float, C.c_float, C.c_float]
     lib.lth_renderer_create.argtypes = [C.c_int]
     lib.lth_renderer_destroy.argtypes = [vp, C.c_int]
+    lib.lth_renderer_cached_scenes.argtypes = [vp, C.c_int]
+    lib.lth_renderer_cached_scenes.restype = C.c_uint64
     lib.lth_render.argtypes = [vp, C.c_int, C.c_char_p, C.c_int, C.c_int, u64, u64, u64, u64, u64, vp, u64, vp, vp, vp,
                                vp]
     lib.lth_render.restype = None
@@ -159,6 +161,9 @@ class Renderer:
                             width, height, depth, out.ctypes.data, out.nbytes, accel.h, model.h, camera.h,
                             C.addressof(ext) if ext is not None else None)
         return out
+
+    def cached_scenes(self):
+        return int(self.lib.lth_renderer_cached_scenes(self.h, self.platform))
 
     def close(self):
         if self.h:

@@ -93,6 +93,7 @@ struct Builder {
 
 AccelerationStructureExplicit::AccelerationStructureExplicit(
     AccelerationStructureExplicitProperties accelerationStructureExplicitProperties) {
+  uniqueId = lt::newObjectId();
   Model* pModel = (Model*)accelerationStructureExplicitProperties.pModel;
   std::vector<PrimitiveInfo>& infos = *pModel->getPrimitiveInfoListP();
   const Material* materials = (const Material*)pModel->getMaterialBuffer();
@@ -164,7 +165,7 @@ AccelerationStructureExplicit::AccelerationStructureExplicit(
   infos.swap(reordered);
 }
 
-AccelerationStructureExplicit::~AccelerationStructureExplicit() {}
+AccelerationStructureExplicit::~AccelerationStructureExplicit() { lt::retireObjectId(uniqueId); }
 
 uint64_t AccelerationStructureExplicit::getNodeBufferSize() { return sizeof(LinearBVHNode) * linearNodes.size(); }
 void* AccelerationStructureExplicit::getNodeBuffer() { return linearNodes.data(); }

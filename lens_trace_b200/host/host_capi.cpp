@@ -60,6 +60,11 @@ void lth_renderer_destroy(void* renderer, int platform) {
   else delete (RendererOpenCL*)renderer;
 }
 
+uint64_t lth_renderer_cached_scenes(void* renderer, int platform) {
+  RendererB200* r = platform == 1 ? ((RendererCUDA*)renderer)->b200() : ((RendererOpenCL*)renderer)->b200();
+  return r ? r->cachedSceneCount() : 0;
+}
+
 void lth_render(void* renderer, int platform, const char* kernel_file_path, int kernel_mode, int thread_org_mode,
                 uint64_t bx, uint64_t by, uint64_t width, uint64_t height, uint64_t depth, float* out,
                 uint64_t out_bytes, void* as, void* model, void* camera, void* ext) {

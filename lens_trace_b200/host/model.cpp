@@ -7,6 +7,7 @@
 #include <algorithm>
 
 Model::Model(std::string fileName) {
+  this->uniqueId = lt::newObjectId();
   this->fileName = Resource::findResource(fileName);
   this->success = tinyobj::LoadObj(&this->attrib, &this->shapes, &this->materials, &this->warning, &this->error,
                                    this->fileName.c_str());
@@ -56,7 +57,7 @@ Model::Model(std::string fileName) {
   }
 }
 
-Model::~Model() {}
+Model::~Model() { lt::retireObjectId(this->uniqueId); }
 
 std::string Model::getFileName() { return this->fileName; }
 

@@ -9,9 +9,45 @@
 #include "lens_trace/resource.h"
 #include "lens_trace_b200.h"
 
-bool RendererB200::SceneKey::operator<(const SceneKey& o) const { return memcmp(this, &o, sizeof(SceneKey)) < 0; }
+#include <atomic>
+#include <mutex>
+#include <set>
 
-RendererB200::RendererB200() : ctx(nullptr) {
+// ---- object identity for the device-scene cache (include/lens_trace/api.h) ----
+namespace {
+std::atomic<uint64_t> g_nextObjectId(1);
+std::atomic<uint64_t> g_retireGeneration(0);
+std::mutex g_retiredMutex;
+std::set<uint64_t> g_retired;  // ids of destroyed objects; consulted only when the generation moved
+
+// FNV-1a over the sizes, the whole light container, the materials (small) and up to 16 KB from both ends and the
+// middle of the node and primitive arrays: cheap enough for every render() call (the reference re-uploads
+// everything per call, src/cuda/renderer_cuda.cpp:90-104), and an in-place edit of a few records that it misses
+// can be forced through forgetScenes().
+uint64_t fnv(uint64_t h, const void* p, size_t n) {
+  const unsigned char* b = (const unsigned char*)p;
+  for (size_t i = 0; i < n; i++) h = (h ^ b[i]) * 1099511628211ull;
+  return h;
+}
+uint64_t sample(uint64_t h, const void* p, uint64_t bytes) {
+  const uint64_t chunk = 16 * 1024;
+  h = fnv(h, &bytes, sizeof bytes);
+  if (bytes <= 3 * chunk) return fnv(h, p, (size_t)bytes);
+  const char* c = (const char*)p;
+  h = fnv(h, c, chunk);
+  h = fnv(h, c + ((bytes / 2) & ~(uint64_t)63), chunk);
+  return fnv(h, c + bytes - chunk, chunk);
+}
+}  // namespace
+
+uint64_t lt::newObjectId() { return g_nextObjectId.fetch_add(1); }
+void lt::retireObjectId(uint64_t id) {
+  std::lock_guard<std::mutex> lock(g_retiredMutex);
+  g_retired.insert(id);
+  g_retireGeneration.fetch_add(1);
+}
+
+RendererB200::RendererB200() : ctx(nullptr), useCounter(0), seenRetireGeneration(0) {
   if (lt_ctx_create(0, &ctx) != LT_OK) {
     printf("ERROR: %s\n", lt_last_error(nullptr));
     ctx = nullptr;
@@ -24,8 +60,7 @@ RendererB200::~RendererB200() {
 }
 
 void RendererB200::forgetScenes() {
-  for (std::map<SceneKey, lt_scene*>::iterator it = sceneCache.begin(); it != sceneCache.end(); ++it)
-    lt_scene_release(ctx, it->second);
+  for (size_t i = 0; i < sceneCache.size(); i++) lt_scene_release(ctx, sceneCache[i].scene);
   sceneCache.clear();
 }
 
@@ -76,26 +111,56 @@ void RendererB200::renderCommon(const std::string& kernelFilePath, KernelMode ke
     }
   }
 
-  SceneKey key;
-  memset(&key, 0, sizeof key);
-  key.nodes = as->getNodeBuffer();
-  key.prims = as->getOrderedPrimitiveBuffer();
-  key.materials = model->getMaterialBuffer();
-  key.nodeBytes = as->getNodeBufferSize();
-  key.primBytes = as->getOrderedPrimitiveBufferSize();
-  key.materialBytes = model->getMaterialBufferSize();
+  // device copy of this (acceleration structure, model) pair: see CachedScene in api.h
+  const uint64_t generation = g_retireGeneration.load();
+  if (generation != seenRetireGeneration) {  // some object was destroyed: drop what we hold for it
+    std::lock_guard<std::mutex> lock(g_retiredMutex);
+    for (size_t i = 0; i < sceneCache.size();) {
+      if (g_retired.count(sceneCache[i].asId) || g_retired.count(sceneCache[i].modelId)) {
+        lt_scene_release(ctx, sceneCache[i].scene);
+        sceneCache.erase(sceneCache.begin() + i);
+      } else {
+        i++;
+      }
+    }
+    seenRetireGeneration = generation;
+  }
+  uint64_t checksum = 14695981039346656037ull;
+  checksum = sample(checksum, as->getNodeBuffer(), as->getNodeBufferSize());
+  checksum = sample(checksum, as->getOrderedPrimitiveBuffer(), as->getOrderedPrimitiveBufferSize());
+  checksum = sample(checksum, model->getMaterialBuffer(), model->getMaterialBufferSize());
+  checksum = sample(checksum, as->getLightContainerBuffer(), as->getLightContainerBufferSize());
   lt_scene* scene = nullptr;
-  std::map<SceneKey, lt_scene*>::iterator sc = sceneCache.find(key);
-  if (sc != sceneCache.end()) {
-    scene = sc->second;
-  } else {
-    int rc = lt_scene_upload(ctx, key.nodes, key.nodeBytes, key.prims, key.primBytes, key.materials, key.materialBytes,
-                             as->getLightContainerBuffer(), as->getLightContainerBufferSize(), &scene);
+  for (size_t i = 0; i < sceneCache.size(); i++) {
+    CachedScene& c = sceneCache[i];
+    if (c.asId != as->getUniqueId() || c.modelId != model->getUniqueId()) continue;
+    if (c.checksum == checksum) {
+      scene = c.scene;
+      c.lastUse = ++useCounter;
+    } else {  // edited in place since the upload
+      lt_scene_release(ctx, c.scene);
+      sceneCache.erase(sceneCache.begin() + i);
+    }
+    break;
+  }
+  if (!scene) {
+    int rc = lt_scene_upload(ctx, as->getNodeBuffer(), as->getNodeBufferSize(), as->getOrderedPrimitiveBuffer(),
+                             as->getOrderedPrimitiveBufferSize(), model->getMaterialBuffer(),
+                             model->getMaterialBufferSize(), as->getLightContainerBuffer(),
+                             as->getLightContainerBufferSize(), &scene);
     if (rc != LT_OK) {
       printf("ERROR: scene upload failed: %s\n", lt_last_error(ctx));
       return;
     }
-    sceneCache[key] = scene;
+    if (sceneCache.size() >= kMaxScenes) {  // bounded: the least recently used device copy goes
+      size_t oldest = 0;
+      for (size_t i = 1; i < sceneCache.size(); i++)
+        if (sceneCache[i].lastUse < sceneCache[oldest].lastUse) oldest = i;
+      lt_scene_release(ctx, sceneCache[oldest].scene);
+      sceneCache.erase(sceneCache.begin() + oldest);
+    }
+    CachedScene c = {as->getUniqueId(), model->getUniqueId(), checksum, ++useCounter, scene};
+    sceneCache.push_back(c);
   }
 
   RenderExtensionB200* ext = nullptr;

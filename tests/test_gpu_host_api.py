@@ -285,3 +285,87 @@ def test_plugin_device_api_lt_trace():
             assert set(np.unique(got[..., 2]).tolist()) <= {0.0, 1.0} and got[..., 2][m].max() == 1.0
         sc.release()
     ctx.close()
+
+
+def test_registry_goes_by_content_through_the_renderer(tmp_path):
+    """a user who edits basic.cu (the reference's custom-kernel mechanism) must get THEIR kernel, not
+    the built-in pipeline of that name; an edited .cl is a reported error that leaves the buffer untouched."""
+    ref_cu = os.path.join(util.ROOT, "oracle", "_ref", "resources", "kernels", "cuda", "basic.cu")
+    if not os.path.exists(ref_cu):
+        pytest.skip("oracle/_ref not built")
+    os.chdir(util.ROOT)
+    cam = host.Camera(0, 2.5, -50, 0)
+    model = host.Model("resources/models/cornell_box.obj")
+    accel = host.AccelerationStructure(model)
+    r = host.Renderer(host.PLATFORM_CUDA)
+    w, h = 160, 120
+    builtin = r.render("resources/kernels/cuda/basic.cu", w, h, accel, model, cam)
+    text = open(ref_cu).read()
+    # the unmodified reference text under another directory: recognised by content -> built-in pipeline
+    (tmp_path / "a").mkdir()
+    same = tmp_path / "a" / "basic.cu"
+    same.write_text(text)
+    from lens_trace_b200 import capi
+    assert capi.kernel_from_path(str(same)) == L.KERNEL_BASIC_CU
+    util.assert_bit_equal(r.render(str(same), w, h, accel, model, cam), builtin)
+    # same NAME, edited colour store: must run as a plug-in and show the edit
+    (tmp_path / "b").mkdir()
+    edited = tmp_path / "b" / "basic.cu"
+    assert text.count("output[id + 0] = outputColor.x;") == 1
+    edited.write_text(text.replace("output[id + 0] = outputColor.x;", "output[id + 0] = outputColor.x * 0.5f + 0.25f;"))
+    assert capi.kernel_from_path(str(edited)) < 0
+    got = r.render(str(edited), w, h, accel, model, cam, block=(8, 8))
+    want = builtin.copy()
+    want[..., 0] = want[..., 0] * np.float32(0.5) + np.float32(0.25)
+    util.assert_bit_equal(got, want, "edited basic.cu runs as the user's kernel")
+    # edited .cl under the shipped name: error, buffer untouched
+    cl = tmp_path / "custom_opencl.cl"
+    cl.write_text("// my own shading\n__kernel void linearKernel() {}\n")
+    out = np.full((h, w, 3), -1, np.float32)
+    host.Renderer(host.PLATFORM_OPENCL).render(str(cl), w, h, accel, model, cam, out=out)
+    assert (out == -1).all()
+    r.close(); accel.close(); model.close(); cam.close()
+
+
+def test_scene_cache_follows_object_identity_and_content():
+    """the device-scene cache was keyed by host addresses.  Now: ids that are never reused + a content
+    checksum; destroyed objects are dropped; at most 8 device scenes are kept."""
+    os.chdir(util.ROOT)
+    cam = host.Camera(0, 2.5, -50, 0)
+    r = host.Renderer(host.PLATFORM_CUDA)
+    K = "resources/kernels/cuda/basic.cu"
+    w, h = 96, 64
+    imgs = {}
+    for name in ("green_wall", "cornell_box"):
+        imgs[name] = O.render(L.KERNEL_BASIC_CU, util.scene(name), util.default_camera(), w, h)
+    # alternate models; every structure is destroyed before the next is created (same addresses are likely reused)
+    for rep in range(6):
+        name = ("green_wall", "cornell_box")[rep % 2]
+        model = host.Model("resources/models/%s.obj" % name)
+        accel = host.AccelerationStructure(model)
+        util.assert_bit_equal(r.render(K, w, h, accel, model, cam), imgs[name], "rep %d %s" % (rep, name))
+        util.assert_bit_equal(r.render(K, w, h, accel, model, cam), imgs[name])
+        accel.close()
+        model.close()
+    assert r.cached_scenes() <= 1  # dead pairs are dropped at the next render()
+    # an in-place edit of the host buffers is seen (checksum), and the bound on live scenes holds
+    model = host.Model("resources/models/green_wall.obj")
+    accel = host.AccelerationStructure(model)
+    before = r.render(K, w, h, accel, model, cam)
+    mats = host._view(host.load().lth_model_material_buffer(model.h), host.load().lth_model_material_bytes(model.h), L.MATERIAL)
+    mats["diffuse"][:] = (0.25, 0.5, 0.75)
+    after = r.render(K, w, h, accel, model, cam)
+    assert (before != after).any() and set(np.unique(after).tolist()) <= {0.0, 0.25, 0.5, 0.75}
+    keep = []
+    for k in range(10):
+        m = host.Model("resources/models/green_wall.obj")
+        a = host.AccelerationStructure(m)
+        r.render(K, w, h, a, m, cam)
+        keep.append((m, a))
+    assert r.cached_scenes() == 8
+    for m, a in keep:
+        a.close()
+        m.close()
+    r.render(K, w, h, accel, model, cam)
+    assert r.cached_scenes() == 1
+    r.close(); accel.close(); model.close(); cam.close()

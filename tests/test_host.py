@@ -35,18 +35,57 @@ def test_no_silent_cpu_fallback():
     assert "no CUDA device" in str(e.value) and "no CPU fallback" in str(e.value)
 
 
-def test_kernel_registry():
+def test_kernel_registry(tmp_path):
+    """kernelFilePath -> pipeline goes by the file's content, never by its name (renderer_cuda.cpp:20-39,52-55
+    compiles whatever the file holds)."""
     k = capi.kernel_from_path
-    assert k("resources/kernels/cuda/basic.cu") == L.KERNEL_BASIC_CU
-    assert k("resources/kernels/opencl/basic.cl") == L.KERNEL_BASIC_CL
-    assert k("resources/kernels/custom_opencl.cl") == L.KERNEL_CUSTOM_BARY
-    assert k("resources/kernels/opencl/basic_lighting.cl") == L.KERNEL_LIGHTING25
-    assert k("resources/kernels/accumulator.cl") == L.KERNEL_ACCUMULATOR
-    assert k("/nonexistent/resources/kernels/opencl/global_illumination.cl") == L.KERNEL_GI25
-    assert k("/nonexistent/resources/kernels/global_illumination.cl") == L.KERNEL_GI
-    assert k(os.path.join(util.ROOT, "resources/kernels/opencl/global_illumination.cl")) == L.KERNEL_GI25
-    assert k(os.path.join(util.ROOT, "examples/global_illumination/resources/kernels/global_illumination.cl")) == L.KERNEL_GI
-    assert k("my_own_kernel.cl") < 0  # unknown .cl is an error, not a fallback
+    R = util.ROOT
+    assert k(os.path.join(R, "resources/kernels/cuda/basic.cu")) == L.KERNEL_BASIC_CU
+    assert k(os.path.join(R, "resources/kernels/opencl/basic.cl")) == L.KERNEL_BASIC_CL
+    assert k(os.path.join(R, "examples/custom_kernel/resources/kernels/custom_opencl.cl")) == L.KERNEL_CUSTOM_BARY
+    assert k(os.path.join(R, "resources/kernels/opencl/basic_lighting.cl")) == L.KERNEL_LIGHTING25
+    assert k(os.path.join(R, "examples/accumulator/resources/kernels/accumulator.cl")) == L.KERNEL_ACCUMULATOR
+    assert k(os.path.join(R, "resources/kernels/opencl/global_illumination.cl")) == L.KERNEL_GI25
+    assert k(os.path.join(R, "examples/global_illumination/resources/kernels/global_illumination.cl")) == L.KERNEL_GI
+    assert k("/nonexistent/resources/kernels/cuda/basic.cu") < 0  # unreadable: nothing to go by
+    assert k("my_own_kernel.cl") < 0
+    # a descriptor under any name selects its pipeline; the same name with other content does not
+    d = tmp_path / "whatever.cl"
+    d.write_text("// my scene\n// lt-pipeline: gi25\n")
+    assert k(str(d)) == L.KERNEL_GI25
+    edited = tmp_path / "basic.cu"
+    edited.write_text(open(os.path.join(R, "resources/kernels/cuda/basic.cu")).read() +
+                      'extern "C" __global__ void linearKernel() {}\n')
+    assert k(str(edited)) < 0  # descriptor tag + code = a user kernel
+    cl = tmp_path / "custom_opencl.cl"
+    cl.write_text("__kernel void linearKernel() {}\n")
+    assert k(str(cl)) < 0
+
+
+REF_KERNELS = [("resources/kernels/cuda/basic.cu", L.KERNEL_BASIC_CU),
+               ("resources/kernels/opencl/basic.cl", L.KERNEL_BASIC_CL),
+               ("examples/custom_kernel/resources/kernels/custom_opencl.cl", L.KERNEL_CUSTOM_BARY),
+               ("resources/kernels/opencl/basic_lighting.cl", L.KERNEL_LIGHTING25),
+               ("examples/accumulator/resources/kernels/accumulator.cl", L.KERNEL_ACCUMULATOR),
+               ("resources/kernels/opencl/global_illumination.cl", L.KERNEL_GI25),
+               ("examples/global_illumination/resources/kernels/global_illumination.cl", L.KERNEL_GI)]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="the reference tree is only present in the build container")
+def test_kernel_registry_recognises_the_reference_text(tmp_path):
+    """The reference's own kernel files (unmodified, also with CRLF line ends, under any name) select the built-in
+    pipeline; one changed character makes the file a user kernel."""
+    k = capi.kernel_from_path
+    for rel, kernel in REF_KERNELS:
+        src = os.path.join("/root/reference", rel)
+        assert k(src) == kernel, rel
+        text = open(src, "rb").read()
+        crlf = tmp_path / ("crlf_" + os.path.basename(rel))
+        crlf.write_bytes(text.replace(b"\n", b"\r\n"))
+        assert k(str(crlf)) == kernel
+        edited = tmp_path / os.path.basename(rel)
+        edited.write_bytes(text.replace(b"0.5", b"0.4", 1) if b"0.5" in text else text + b"\n// x\n")
+        assert k(str(edited)) < 0, rel
 
 
 def test_cornell_box_loads_like_the_reference():
@@ -311,3 +350,13 @@ def test_threaded_tree_is_the_reference_traversal_order(tmp_path):
         for trial in range(40):
             o3, inv, neg = _random_ray(rng, trial)
             assert _threaded_walk(T, n, o3, inv, neg) == _reference_walk(nodes, o3, inv, neg)
+
+
+def test_unreachable_node_entries_are_rejected_on_the_host():
+    """validate_tree (lt_scene_upload, lt_debug_build_threaded): every array entry must be reachable from the root."""
+    sb = util.scene("cornell_box")
+    capi.build_threaded(sb.nodes)
+    padded = np.concatenate([sb.nodes, sb.nodes[-1:]])
+    with pytest.raises(capi.LtError) as e:
+        capi.build_threaded(padded)
+    assert "reachable" in str(e.value)
