@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define LT_API_VERSION 1
+#define LT_API_VERSION 2
 
 enum lt_status {
   LT_OK = 0,
@@ -68,8 +68,8 @@ enum lt_flags {
                                   both produce bit-identical output) */
   LT_FLAG_SERIAL = 1 << 5,     /* wavefront pipeline: one stream, one kernel at a time (default: consecutive batches
                                   overlap on two streams; identical output).  For timing kernels in isolation. */
-  LT_FLAG_NO_STREAM = 1 << 6,  /* one thread per pixel (k_flat / fixed pixels in k_path) instead of the persistent
-                                  kernels that deal pixels to idle lanes (identical output; kept for comparison) */
+  LT_FLAG_NO_STREAM = 1 << 6,  /* deterministic kernels on large scenes: one thread per pixel (k_flat) instead of the
+                                  persistent warps that fetch pixel tiles (identical output; kept for comparison) */
   LT_FLAG_NO_THREADED = 1 << 4 /* small scenes: traverse with the stack kernels instead of the stackless threaded
                                   tree (default for scenes whose 8 octant copies stay cache resident; identical
                                   output, kept selectable so tests can compare the two) */
@@ -106,6 +106,12 @@ typedef struct lt_stats {
   float trace_ms;       /* part of kernel_ms spent in the traversal kernels (k_wf_primary + k_wf_trace, or the
                            whole megakernel), CUDA events around each launch; 0 when the call was not synchronous */
   int32_t trace_launches;
+  /* API version 2: per-kernel times of a wavefront step whose kernels ran one at a time (LT_FLAG_SERIAL or
+     LT_FLAG_STATS, synchronous call), CUDA events around each launch; 0 otherwise */
+  float shade_ms;          /* k_wf_shade launches */
+  float primary_shade_ms;  /* k_wf_primary launches that shade shared camera-ray hits (no traversal) */
+  float accumulate_ms;     /* k_wf_accumulate launches */
+  int32_t shade_launches;
 } lt_stats;
 
 /* --- context: replaces RendererCUDA::RendererCUDA() (src/cuda/renderer_cuda.cpp:10-14). --- */

@@ -39,7 +39,8 @@ class Stats(C.Structure):
     _fields_ = [
         ("rays", C.c_uint64), ("node_tests", C.c_uint64), ("tri_tests", C.c_uint64), ("kernel_ms", C.c_float),
         ("upload_ms", C.c_float), ("kernel_launches", C.c_int32), ("sm_count", C.c_int32), ("trace_ms", C.c_float),
-        ("trace_launches", C.c_int32),
+        ("trace_launches", C.c_int32), ("shade_ms", C.c_float), ("primary_shade_ms", C.c_float),
+        ("accumulate_ms", C.c_float), ("shade_launches", C.c_int32),
     ]
 
 

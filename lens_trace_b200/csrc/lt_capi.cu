@@ -21,7 +21,8 @@ struct lt_ctx {
   size_t outFloats = 0;
   LtCounters* dCounters = nullptr;
   int* dWork = nullptr;  // work counters of the persistent kernels
-  std::vector<cudaEvent_t> traceEvents;  // pairs of events around traversal launches (timed when synchronous)
+  std::vector<cudaEvent_t> traceEvents;  // pairs of events around launches (timed when synchronous)
+  std::vector<unsigned char> pairKinds;  // LT_TIMED_* of every pair
   std::vector<LtPlugin*> plugins;  // compiled user kernels, by id
   RefCamera* dCamera = nullptr;    // camera buffer for plug-in launches
   void* wfWorkspace = nullptr;  // wavefront path state / ray queues (two batch workspaces when batches overlap)
@@ -612,18 +613,22 @@ static int render_common(lt_ctx* ctx, lt_scene* scene, const LtLaunch& L, float*
       }
     }
   }
-  const int kMaxTracePairs = 2048;
+  const int kMaxTracePairs = 8192;
   int tracePairs = 0;
   bool timeTrace = wavefront && (sync || stats);
   if (timeTrace && ctx->traceEvents.empty()) {
     ctx->traceEvents.resize(2 * kMaxTracePairs);
+    ctx->pairKinds.resize(kMaxTracePairs);
     for (size_t i = 0; i < ctx->traceEvents.size(); i++) cudaEventCreate(&ctx->traceEvents[i]);
   }
+  // per-kernel times are only defined when one kernel runs at a time (LT_FLAG_SERIAL / stats launches)
+  const bool timeKinds = timeTrace && (!overlapBatches);
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
   int launches = wavefront ? lt_launch_render_wavefront(scene->dev, L, dOut, ctx->dCounters, ctx->wfWorkspace,
                                                         batchFrames, ctx->stats.sm_count, ctx->stream,
                                                         timeTrace ? ctx->traceEvents.data() : nullptr, kMaxTracePairs,
-                                                        &tracePairs, overlapBatches ? &ctx->wfAux : nullptr)
+                                                        &tracePairs, timeKinds ? ctx->pairKinds.data() : nullptr,
+                                                        overlapBatches ? &ctx->wfAux : nullptr)
                            : lt_launch_render(scene->dev, L, dOut, ctx->dCounters, ctx->dWork, ctx->stats.sm_count,
                                               ctx->stream);
   CK(cudaGetLastError());
@@ -633,15 +638,30 @@ static int render_common(lt_ctx* ctx, lt_scene* scene, const LtLaunch& L, float*
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaEventElapsedTime(&ctx->stats.kernel_ms, ctx->ev0, ctx->ev1));
     ctx->stats.trace_ms = wavefront ? 0.0f : ctx->stats.kernel_ms;
-    ctx->stats.trace_launches = wavefront ? tracePairs : 1;
+    ctx->stats.trace_launches = wavefront ? 0 : 1;
+    ctx->stats.shade_ms = ctx->stats.primary_shade_ms = ctx->stats.accumulate_ms = 0.0f;
+    ctx->stats.shade_launches = 0;
     for (int i = 0; i < tracePairs; i++) {
       float ms = 0.0f;
       cudaEventElapsedTime(&ms, ctx->traceEvents[2 * i], ctx->traceEvents[2 * i + 1]);
-      ctx->stats.trace_ms += ms;
+      const int kind = timeKinds ? ctx->pairKinds[i] : LT_TIMED_TRAVERSAL;
+      if (kind == LT_TIMED_TRAVERSAL) {
+        ctx->stats.trace_ms += ms;
+        ctx->stats.trace_launches++;
+      } else if (kind == LT_TIMED_SHADE) {
+        ctx->stats.shade_ms += ms;
+        ctx->stats.shade_launches++;
+      } else if (kind == LT_TIMED_PRIMARY_SHADE) {
+        ctx->stats.primary_shade_ms += ms;
+      } else {
+        ctx->stats.accumulate_ms += ms;
+      }
     }
   } else {
     ctx->stats.trace_ms = 0.0f;
     ctx->stats.trace_launches = 0;
+    ctx->stats.shade_ms = ctx->stats.primary_shade_ms = ctx->stats.accumulate_ms = 0.0f;
+    ctx->stats.shade_launches = 0;
   }
   if (stats) {
     LtCounters h;

@@ -61,10 +61,13 @@ struct LtWfAux {
   cudaStream_t extra[LT_WF_MAX_STREAMS];    // [0] unused: side 0 runs on the caller's stream
   cudaEvent_t fork, order[LT_WF_MAX_STREAMS];
 };
+// pairKinds: optional, one LT_TIMED_* per recorded pair; when given, the shade / primary-shade / accumulate launches
+// are bracketed as well (per-kernel times of a serialised step)
+enum { LT_TIMED_TRAVERSAL = 0, LT_TIMED_SHADE = 1, LT_TIMED_PRIMARY_SHADE = 2, LT_TIMED_ACCUMULATE = 3, LT_TIMED_KINDS = 4 };
 int lt_launch_render_wavefront(const LtSceneDev& sc, const LtLaunch& L, float* dOut, LtCounters* dCounters,
                                void* workspace, int batchFrames, int smCount, cudaStream_t stream,
                                cudaEvent_t* traceEvents, int maxTraceLaunches, int* traceLaunches,
-                               const LtWfAux* aux);
+                               unsigned char* pairKinds, const LtWfAux* aux);
 
 // user-written CUDA kernels with the reference's plug-in ABI (lt_plugin.cu)
 #include <string>

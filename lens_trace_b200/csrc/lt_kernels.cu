@@ -66,121 +66,77 @@ __global__ void __launch_bounds__(LT_BLOCK) k_flat(LtSceneDev sc, LtLaunch L, fl
   }
 }
 
-// Persistent form of k_flat for the exact, uncounted launches: blocks stay resident (SMs x blocks per SM), a warp
-// claims runs of pixels from a global counter -- enumerated as 8x4 tiles so that the rays a warp holds stay
-// neighbours -- and deals them to whichever lanes are idle, so no lane, warp or SM waits for the longest ray of a
-// fixed pixel tile (ncu on the 1 M-triangle mesh: with one ray per thread the SMs were active 45 % of the kernel's
-// duration, profiles/r2a_*).  Rays run through the same software-pipelined traversal as k_wf_trace; the lens path
-// (basic.cu:245-298) is two more rays of the same lane.  Same tests in the same order per ray as k_flat, hence the
-// same picture (tests compare the two through LT_FLAG_NO_STREAM).
-template <bool THREADED>
+// Persistent form of k_flat for the exact, uncounted launches on large scenes.  Blocks stay resident (SMs x blocks
+// per SM) and every WARP takes the next 8x4 pixel tile from a global counter when all its rays are done.  Measured
+// on the 1 M-triangle mesh, 1080p primary rays (profiles/r2a_*, tools/ray_length_histogram.py): with a fixed
+// 16x8 tile per block the SMs were active 45 % of the kernel's duration (0.99 ms; the rays of the height field make
+// 733 dependent box-pair steps, those of the walls 22) -- warps that fetch tiles on their own: 0.73 ms.  Dealing
+// single pixels to idle lanes (as k_wf_trace deals queue entries) was measured too and LOSES, 1.83 ms: the camera
+// rays of a tile walk the tree together (lane utilisation 0.90) and share its cache lines.  Rays run through the
+// same software-pipelined traversal as k_wf_trace; the lens path (basic.cu:245-298) is two more rays of the same
+// lane.  Same tests in the same order per ray as k_flat, hence the same picture (LT_FLAG_NO_STREAM selects k_flat;
+// tests compare the two).
 __global__ void __launch_bounds__(LT_BLOCK) k_flat_stream(LtSceneDev sc, LtLaunch L, float* __restrict__ out,
                                                           int* __restrict__ work) {
   extern __shared__ int smemStack[];
   int* stk = smemStack + threadIdx.x;
-  int* list = smemStack + (THREADED ? 0 : lt_stack_levels(sc) * LT_BLOCK) + threadIdx.x;
+  int* list = smemStack + lt_stack_levels(sc) * LT_BLOCK + threadIdx.x;
   const unsigned stkAddr = (unsigned)__cvta_generic_to_shared(stk);
   const unsigned fifoAddr = (unsigned)__cvta_generic_to_shared(list);
   const unsigned lane = threadIdx.x & 31u;
   const float tInit = lt_tinit(L.kernel), epsThr = lt_eps(L.kernel);
   const float camC = cosf(L.cam.yaw), camS = sinf(L.cam.yaw);
   const int tilesX = (L.width + 7) >> 3, tilesY = (L.height + 3) >> 2;
-  const int n = tilesX * tilesY * 32;  // entries: tile-major, 32 per 8x4 tile (entries off the image are skipped)
+  const int nTiles = tilesX * tilesY;
   LtCounters cnt = {0, 0, 0};
-  Trav t;
-  t.cur = LT_DONE;
-  int pixel = -1;      // py * width + px of the lane's current pixel, -1 = idle
-  int stage = 0;       // 0 camera ray, 1 first lens ray, 2 second lens ray
-  int baseMat = 0;     // material of the camera ray's hit (kept when the lens path ends in a miss)
-  float r2w = 0.0f;
-  int chunkNext = 0, chunkEnd = 0;
-  bool exhausted = false;
   while (true) {
-    bool has = pixel >= 0;
-    unsigned need = __ballot_sync(0xffffffffu, !has);
-    if (__popc(need) >= L.refillThreshold && !exhausted) {
-      if (chunkNext >= chunkEnd) {
-        int base = 0;
-        if (lane == 0u) base = atomicAdd(work, L.batchClosest);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        chunkNext = base;
-        chunkEnd = min(base + L.batchClosest, n);
-        if (base >= n) exhausted = true;
+    int tile = 0;
+    if (lane == 0u) tile = atomicAdd(work, 1);
+    tile = __shfl_sync(0xffffffffu, tile, 0);
+    if (tile >= nTiles) break;
+    const int ty = tile / tilesX, tx = tile - ty * tilesX;
+    const int px = (tx << 3) + (int)(lane & 7u), py = (ty << 2) + (int)(lane >> 3);
+    if (px >= L.width || py >= L.height) continue;  // (the other lanes of the warp run their pixels; no barrier follows)
+    float fx, fy;
+    Trav t;
+    t.r = camera_ray_cs(L.cam, camC, camS, px, py, L.width, L.height, fx, fy);
+    float color[3] = {0.0f, 0.0f, 0.0f};
+    int baseMat = 0;  // material of the camera ray's hit (kept when the lens path ends in a miss)
+    float r2w = 0.0f;
+    int ignore = -1;
+    for (int stage = 0; stage < 3; stage++) {  // 0 camera ray, 1 and 2 the rays through a lens (basic.cu:245-298)
+      trav_begin<false>(t, sc, ignore, tInit, false, cnt);
+      while (!trav_iter_lean<false>(t, sc, stkAddr, fifoAddr, epsThr, L.iterNodeSteps, L.iterTriTests, cnt)) {
       }
-      if (!exhausted) {
-        int idx = chunkNext + __popc(need & ((1u << lane) - 1u));
-        chunkNext += __popc(need);
-        if (!has && idx < chunkEnd) {
-          int tile = idx >> 5, l = idx & 31;
-          int ty = tile / tilesX, tx = tile - ty * tilesX;
-          int px = (tx << 3) + (l & 7), py = (ty << 2) + (l >> 3);
-          if (px < L.width && py < L.height) {
-            float fx, fy;
-            t.r = camera_ray_cs(L.cam, camC, camS, px, py, L.width, L.height, fx, fy);
-            if (THREADED) trav_begin_threaded(t, sc, -1, tInit, false);
-            else trav_begin<false>(t, sc, -1, tInit, false, cnt);
-            pixel = py * L.width + px;
-            stage = 0;
-          }
+      const Hit h = t.h;
+      if (stage == 0) {
+        if (h.hit != 1) break;
+        if (L.kernel == 2) {  // custom_opencl.cl:240
+          color[0] = h.u;
+          color[1] = h.v;
+          color[2] = bary0(h.u, h.v);
+          break;
         }
+        baseMat = sc.prims[h.prim].materialIndex;  // basic.cu:312-326
+        if (!(sc.mats[baseMat].dissolve < 1.0f)) break;
+        ignore = lens_refract_in(sc, t.r, h, r2w);
+      } else if (stage == 1) {
+        ignore = lens_refract_out(sc, t.r, h, r2w);
+      } else if (h.hit == 1) {
+        baseMat = sc.prims[h.prim].materialIndex;
       }
     }
-    has = pixel >= 0;
-    if (!__any_sync(0xffffffffu, has)) {
-      if (exhausted) break;
-      continue;
+    if (L.kernel != 2 && (t.h.hit == 1 || ignore >= 0)) {
+      const RefMaterial* mat = sc.mats + baseMat;
+      color[0] = mat->diffuse[0];
+      color[1] = mat->diffuse[1];
+      color[2] = mat->diffuse[2];
     }
-    if (has) {
-      bool finished = t.cur == LT_DONE && t.qHead == t.qTail;  // a ray that missed the root box
-      if (!finished) {
-        if (THREADED) finished = trav_iter_threaded(t, sc.tnodes, sc.tris, fifoAddr, epsThr, L.iterNodeSteps, L.iterTriTests);
-        else finished = trav_iter_lean<false>(t, sc, stkAddr, fifoAddr, epsThr, L.iterNodeSteps, L.iterTriTests, cnt);
-      }
-      if (finished) {
-        bool done = true;
-        float color[3] = {0.0f, 0.0f, 0.0f};
-        if (stage == 0) {
-          if (t.h.hit == 1) {
-            if (L.kernel == 2) {  // custom_opencl.cl:240
-              color[0] = t.h.u;
-              color[1] = t.h.v;
-              color[2] = bary0(t.h.u, t.h.v);
-            } else {  // basic.cu:312-326
-              baseMat = sc.prims[t.h.prim].materialIndex;
-              if (sc.mats[baseMat].dissolve < 1.0f) {
-                const Hit h = t.h;
-                int ignore = lens_refract_in(sc, t.r, h, r2w);
-                if (THREADED) trav_begin_threaded(t, sc, ignore, tInit, false);
-                else trav_begin<false>(t, sc, ignore, tInit, false, cnt);
-                stage = 1;
-                done = false;
-              }
-            }
-          }
-        } else if (stage == 1) {
-          const Hit h = t.h;
-          int ignore = lens_refract_out(sc, t.r, h, r2w);
-          if (THREADED) trav_begin_threaded(t, sc, ignore, tInit, false);
-          else trav_begin<false>(t, sc, ignore, tInit, false, cnt);
-          stage = 2;
-          done = false;
-        }
-        if (done) {
-          if (L.kernel != 2 && (stage != 0 || t.h.hit == 1)) {
-            const RefMaterial* mat = sc.mats + ((stage == 2 && t.h.hit == 1) ? sc.prims[t.h.prim].materialIndex : baseMat);
-            color[0] = mat->diffuse[0];
-            color[1] = mat->diffuse[1];
-            color[2] = mat->diffuse[2];
-          }
-          long long id = (long long)pixel * L.depth;
-          FrameSink sink;
-          sink.begin(L, out, id);
-          for (int f = 0; f < L.frames; f++) sink.frame(L, L.cam.frameCount + (unsigned)f * L.frameStride, color);
-          sink.end(out, id);
-          pixel = -1;
-        }
-      }
-    }
+    const long long id = ((long long)py * L.width + px) * L.depth;
+    FrameSink sink;
+    sink.begin(L, out, id);
+    for (int f = 0; f < L.frames; f++) sink.frame(L, L.cam.frameCount + (unsigned)f * L.frameStride, color);
+    sink.end(out, id);
   }
 }
 
@@ -194,32 +150,30 @@ __global__ void __launch_bounds__(LT_BLOCK) k_flat_stream(LtSceneDev sc, LtLaunc
 //     for a new ray, so long rays never hold the other 31 lanes idle.  Traversal state is resumable.
 template <bool STATS>
 __global__ void __launch_bounds__(LT_BLOCK) k_path(LtSceneDev sc, LtLaunch L, float* __restrict__ out,
-                                                   LtCounters* gcnt, int* __restrict__ work) {
+                                                   LtCounters* gcnt) {
   LT_SMEM_POINTERS(sc)
   (void)tstk;  // the persistent megakernel does not cull (LT_FLAG_CULL selects the wavefront pipeline)
   const unsigned stkAddr = (unsigned)__cvta_generic_to_shared(stk);
   const unsigned fifoAddr = (unsigned)__cvta_generic_to_shared(list);
-  const unsigned lane = threadIdx.x & 31u;
+  int px, py;
+  bool alive = thread_pixel(L.width, L.height, px, py);
   LtCounters cnt = {0, 0, 0};
   const PathConsts pc = path_consts(L);
-  // work == nullptr: one thread per pixel of a 16x8 tile per block (grid = tiles).  Otherwise the blocks are
-  // persistent and a lane whose pixel has finished all its frames takes the next pixel from a global counter
-  // (8x4 tiles, like k_flat_stream): on large scenes the fixed assignment left SMs idle behind the slowest tiles.
-  const bool dynamic = work != nullptr;
-  const float camC = cosf(L.cam.yaw), camS = sinf(L.cam.yaw);
-  const int tilesX = (L.width + 7) >> 3, tilesY = (L.height + 3) >> 2;
-  const int nEntries = tilesX * tilesY * 32;
-  int chunkNext = 0, chunkEnd = 0;
-  bool exhausted = !dynamic;
 
   float fx = 0.0f, fy = 0.0f;
   Ray cameraRay = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 1.0f};
   long long id = 0;
   FrameSink sink;
   sink.acc[0] = sink.acc[1] = sink.acc[2] = 0.0f;
+  if (alive) {
+    cameraRay = camera_ray(L.cam, px, py, L.width, L.height, fx, fy);
+    id = ((long long)py * L.width + px) * L.depth;
+    sink.begin(L, out, id);
+  }
+
   int frame = 0, sample = 0;
   float frameColor[3] = {0.0f, 0.0f, 0.0f};
-  unsigned sampleIndex = 0u;
+  unsigned sampleIndex = (pc.samplesPerFrame == 25) ? L.cam.frameCount * 32u : L.cam.frameCount;
   PathState ps;
   ps.nrm[0] = ps.nrm[1] = ps.nrm[2] = 0.0f;
   ps.diffuse[0] = ps.diffuse[1] = ps.diffuse[2] = 0.0f;
@@ -231,52 +185,14 @@ __global__ void __launch_bounds__(LT_BLOCK) k_path(LtSceneDev sc, LtLaunch L, fl
   const bool threaded = !STATS && sc.tnodes != nullptr;  // small scene: stackless threaded tree, same tests
   Trav t;
   t.r = cameraRay;
-  t.cur = LT_DONE;
-  bool traversing = false, alive = false;
-  int px = 0, py = 0;
-  bool fresh = !dynamic && thread_pixel(L.width, L.height, px, py);  // this lane was just given pixel (px, py)
+  bool traversing = false;
+  if (alive) {
+    if (threaded) trav_begin_threaded(t, sc, -1, pc.tInit, false);
+    else trav_begin<STATS>(t, sc, -1, pc.tInit, false, cnt);
+    traversing = (t.cur != LT_DONE);
+  }
 
   while (true) {
-    // ---------------- phase F: idle lanes take the next pixels ----------------
-    if (dynamic && !exhausted) {
-      unsigned need = __ballot_sync(0xffffffffu, !alive);
-      if (__popc(need) >= L.batchAnyHit) {  // (field reused by the dynamic form: idle lanes that trigger a fetch)
-        if (chunkNext >= chunkEnd) {
-          int base = 0;
-          if (lane == 0u) base = atomicAdd(work, 128);
-          base = __shfl_sync(0xffffffffu, base, 0);
-          chunkNext = base;
-          chunkEnd = min(base + 128, nEntries);
-          if (base >= nEntries) exhausted = true;
-        }
-        if (!exhausted) {
-          int idx = chunkNext + __popc(need & ((1u << lane) - 1u));
-          chunkNext += __popc(need);
-          if (!alive && idx < chunkEnd) {
-            int tile = idx >> 5, l = idx & 31;
-            int ty = tile / tilesX, tx = tile - ty * tilesX;
-            px = (tx << 3) + (l & 7);
-            py = (ty << 2) + (l >> 3);
-            fresh = px < L.width && py < L.height;
-          }
-        }
-      }
-    }
-    if (fresh) {
-      fresh = false;
-      alive = true;
-      cameraRay = camera_ray_cs(L.cam, camC, camS, px, py, L.width, L.height, fx, fy);
-      id = ((long long)py * L.width + px) * L.depth;
-      sink.begin(L, out, id);
-      frame = 0;
-      sample = 0;
-      sampleIndex = (pc.samplesPerFrame == 25) ? L.cam.frameCount * 32u : L.cam.frameCount;
-      path_reset(ps);
-      t.r = cameraRay;
-      if (threaded) trav_begin_threaded(t, sc, -1, pc.tInit, false);
-      else trav_begin<STATS>(t, sc, -1, pc.tInit, false, cnt);
-      traversing = (t.cur != LT_DONE);
-    }
     // ---------------- phase S: consume finished rays, generate the next ones ----------------
     while (alive && !traversing) {
       float tStart;
@@ -311,22 +227,18 @@ __global__ void __launch_bounds__(LT_BLOCK) k_path(LtSceneDev sc, LtLaunch L, fl
       else trav_begin<STATS>(t, sc, ignore, tStart, anyHit, cnt);
       traversing = (t.cur != LT_DONE);
     }
-    if (!__any_sync(0xffffffffu, alive)) {
-      if (exhausted) break;
-      continue;
-    }
+    if (!__any_sync(0xffffffffu, alive)) break;
 
     // ---------------- phase T: resumable traversal ----------------
     while (true) {
       unsigned active = __ballot_sync(0xffffffffu, traversing);
       if (active == 0u) break;
-      bool waiting = __any_sync(0xffffffffu, (alive && !traversing) || (!alive && !exhausted));
+      bool waiting = __any_sync(0xffffffffu, alive && !traversing);
       if (waiting && __popc(active) < L.refillThreshold) break;
-      if (!exhausted && __popc(__ballot_sync(0xffffffffu, !alive)) >= L.batchAnyHit) break;
       if (traversing) {
         if (threaded) {
           traversing = !trav_iter_threaded(t, sc.tnodes, sc.tris, fifoAddr, pc.epsThr, 2 * L.iterNodeSteps, L.iterTriTests);
-        } else if (!dynamic && L.batchClosest > 0) {  // leaf-list form: whole batches of box tests, then the recorded triangles
+        } else if (L.batchClosest > 0) {  // leaf-list form: whole batches of box tests, then the recorded triangles
           int n = trav_collect<STATS>(t, sc, stk, list, t.anyHit ? L.batchAnyHit : L.batchClosest, cnt);
           trav_test<STATS>(t, sc, list, n, pc.epsThr, cnt);
           traversing = (t.cur != LT_DONE);
@@ -474,7 +386,7 @@ static void opt_in_smem(size_t smem) {
   cudaFuncSetAttribute(k_path<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_MAX_TRAVERSAL_SMEM);
   cudaFuncSetAttribute(k_path<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_MAX_TRAVERSAL_SMEM);
   cudaFuncSetAttribute(k_primary_hits, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_MAX_TRAVERSAL_SMEM);
-  cudaFuncSetAttribute(k_flat_stream<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_MAX_TRAVERSAL_SMEM);
+  cudaFuncSetAttribute(k_flat_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_MAX_TRAVERSAL_SMEM);
 }
 
 static int tile_blocks(int width, int height) { return ((width + 15) / 16) * ((height + 7) / 8); }
@@ -500,48 +412,25 @@ int lt_launch_render(const LtSceneDev& scIn, const LtLaunch& L, float* dOut, LtC
   opt_in_smem(smem);
   bool stats = (L.flags & 1) != 0;
   bool flat = (L.kernel <= 2);
-  // exact, uncounted launches of the deterministic pipelines: persistent blocks with per-lane refill
-  if (flat && !(L.flags & (1 | 2 | LT_LAUNCH_FLAG_NO_STREAM)) && dWork != nullptr) {
-    const bool threaded = sc.tnodes != nullptr;
-    const size_t smemStream = threaded ? (size_t)LT_MAX_BATCH * LT_BLOCK * sizeof(int) : smem;
-    int blocksPerSm = (int)((200 * 1024) / smemStream);
-    const int cap = env_int("LT_STREAM_BLOCKS_PER_SM", 8);
-    if (blocksPerSm > cap) blocksPerSm = cap;
+  // exact, uncounted launches of the deterministic pipelines on large scenes: persistent warps fetching tiles
+  if (flat && !(L.flags & (1 | 2 | LT_LAUNCH_FLAG_NO_STREAM)) && dWork != nullptr && sc.tnodes == nullptr &&
+      sc.nodeCount >= env_int("LT_STREAM_MIN_NODES", 100000)) {
+    int blocksPerSm = (int)((200 * 1024) / smem);
+    if (blocksPerSm > 8) blocksPerSm = 8;  // measured 4 .. 10: no difference (the longest tile bounds the kernel)
     if (blocksPerSm < 1) blocksPerSm = 1;
     int grid = smCount * blocksPerSm;
     const int warpsNeeded = (((L.width + 7) >> 3) * ((L.height + 3) >> 2) + 3) / 4;  // blocks of 4 warps, one tile each
     if (grid > warpsNeeded) grid = warpsNeeded;
-    LtLaunch Ls = L;
-    Ls.refillThreshold = env_int("LT_STREAM_REFILL_LANES", 8);
-    Ls.batchClosest = env_int("LT_STREAM_CHUNK", 128);  // entries per work claim
-    if (threaded) Ls.iterNodeSteps = 2 * L.iterNodeSteps;
     cudaMemsetAsync(dWork, 0, sizeof(int), stream);
-    if (threaded) k_flat_stream<true><<<grid, LT_BLOCK, smemStream, stream>>>(sc, Ls, dOut, dWork);
-    else k_flat_stream<false><<<grid, LT_BLOCK, smemStream, stream>>>(sc, Ls, dOut, dWork);
+    k_flat_stream<<<grid, LT_BLOCK, smem, stream>>>(sc, L, dOut, dWork);
     return 1;
   }
   if (flat) {
     if (stats) k_flat<true><<<blocks, LT_BLOCK, smem, stream>>>(sc, L, dOut, dCounters);
     else k_flat<false><<<blocks, LT_BLOCK, smem, stream>>>(sc, L, dOut, nullptr);
   } else {
-    // exact, uncounted launches on large scenes: persistent blocks, lanes take pixels from a global counter
-    const bool dynamicPixels = !stats && dWork != nullptr && !(L.flags & LT_LAUNCH_FLAG_NO_STREAM) &&
-                               (sc.nodeCount > env_int("LT_PATH_DYNAMIC_MIN_NODES", 100000) || env_int("LT_PATH_DYNAMIC", 0));
-    if (dynamicPixels) {
-      int blocksPerSm = (int)((200 * 1024) / smem);
-      const int cap = env_int("LT_PATH_BLOCKS_PER_SM", 5);  // 94 registers: 5 blocks of 128 threads
-      if (blocksPerSm > cap) blocksPerSm = cap;
-      if (blocksPerSm < 1) blocksPerSm = 1;
-      int grid = smCount * blocksPerSm;
-      if (grid > blocks) grid = blocks;
-      LtLaunch Ld = L;
-      Ld.batchAnyHit = env_int("LT_PATH_FETCH_LANES", 8);
-      cudaMemsetAsync(dWork, 0, sizeof(int), stream);
-      k_path<false><<<grid, LT_BLOCK, smem, stream>>>(sc, Ld, dOut, nullptr, dWork);
-      return 1;
-    }
-    if (stats) k_path<true><<<blocks, LT_BLOCK, smem, stream>>>(sc, L, dOut, dCounters, nullptr);
-    else k_path<false><<<blocks, LT_BLOCK, smem, stream>>>(sc, L, dOut, nullptr, nullptr);
+    if (stats) k_path<true><<<blocks, LT_BLOCK, smem, stream>>>(sc, L, dOut, dCounters);
+    else k_path<false><<<blocks, LT_BLOCK, smem, stream>>>(sc, L, dOut, nullptr);
   }
   return 1;
 }

@@ -542,13 +542,20 @@ size_t lt_wf_primary_hits_bytes(long long pixels) {
 int lt_launch_render_wavefront(const LtSceneDev& scIn, const LtLaunch& L, float* dOut, LtCounters* dCounters,
                                void* workspace, int batchFrames, int smCount, cudaStream_t stream,
                                cudaEvent_t* traceEvents, int maxTraceLaunches, int* traceLaunches,
-                               const LtWfAux* aux) {
+                               unsigned char* pairKinds, const LtWfAux* aux) {
   LtSceneDev sc = scIn;
   if (L.flags & (1 | 2 | LT_LAUNCH_FLAG_NO_THREADED)) sc.tnodes = nullptr;  // stats / culled / forced stack traversal
   int pairs = 0;
-  auto mark = [&](int which, cudaStream_t s) {  // which: 0 = before, 1 = after a traversal launch
-    if (traceEvents && pairs < maxTraceLaunches) cudaEventRecord(traceEvents[2 * pairs + which], s);
-    if (which == 1 && traceEvents && pairs < maxTraceLaunches) pairs++;
+  // which: 0 = before, 1 = after a launch; kind (LT_TIMED_*): what the bracketed kernel does.  Traversal launches
+  // are always bracketed when events are given, the other kinds only when the caller passes pairKinds.
+  auto mark = [&](int which, cudaStream_t s, int kind = LT_TIMED_TRAVERSAL) {
+    if (!traceEvents || pairs >= maxTraceLaunches) return;
+    if (kind != LT_TIMED_TRAVERSAL && !pairKinds) return;
+    cudaEventRecord(traceEvents[2 * pairs + which], s);
+    if (which == 1) {
+      if (pairKinds) pairKinds[pairs] = (unsigned char)kind;
+      pairs++;
+    }
   };
   const int pixels = L.width * L.height;
   const bool stats = (L.flags & 1) != 0;
@@ -644,10 +651,11 @@ int lt_launch_render_wavefront(const LtSceneDev& scIn, const LtLaunch& L, float*
     for (int s = 0; s < samples; s++) {
       // round 0 (primary rays) fused into one kernel; its survivors are queue 0
       k_wf_reset<<<1, 1, 0, st>>>(B);
-      if (!primaryHits) mark(0, st);  // a traversal kernel only when it traces the camera rays itself
+      // a traversal kernel only when it traces the camera rays itself
+      mark(0, st, primaryHits ? LT_TIMED_PRIMARY_SHADE : LT_TIMED_TRAVERSAL);
       if (stats) k_wf_primary<true><<<grid, WF_BLOCK, smem, st>>>(sc, Lb, B, nf, pixels, s, dCounters, P);
       else k_wf_primary<false><<<grid, WF_BLOCK, smem, st>>>(sc, Lb, B, nf, pixels, s, nullptr, P);
-      if (!primaryHits) mark(1, st);
+      mark(1, st, primaryHits ? LT_TIMED_PRIMARY_SHADE : LT_TIMED_TRAVERSAL);
       launches += 2;
       int q = 0;
       for (int r = 1; r < rounds; r++) {
@@ -661,8 +669,10 @@ int lt_launch_render_wavefront(const LtSceneDev& scIn, const LtLaunch& L, float*
         else if (threaded) k_wf_trace<false, true><<<persistentBlocks, WF_BLOCK, smemTrace, st>>>(sc, Lq, B, q, nullptr, B.rayO[q], B.rayD[q]);
         else k_wf_trace<false, false><<<persistentBlocks, WF_BLOCK, smem, st>>>(sc, Lq, B, q, nullptr, B.rayO[q], B.rayD[q]);
         mark(1, st);
+        mark(0, st, LT_TIMED_SHADE);
         if (q == 0) k_wf_shade<0><<<grid, WF_BLOCK, 0, st>>>(sc, Lb, B, pixels, 0, s, P);
         else k_wf_shade<1><<<grid, WF_BLOCK, 0, st>>>(sc, Lb, B, pixels, 0, s, P);
+        mark(1, st, LT_TIMED_SHADE);
         k_wf_swap<<<1, 1, 0, st>>>(B, q);
         launches += 3;
         q = 1 - q;
@@ -670,7 +680,9 @@ int lt_launch_render_wavefront(const LtSceneDev& scIn, const LtLaunch& L, float*
     }
     // the frame combiner is applied in frame order: this batch's accumulate follows the previous batch's
     if (overlap && batch > 0) cudaStreamWaitEvent(st, aux->order[(side + nStreams - 1) % nStreams], 0);
+    mark(0, st, LT_TIMED_ACCUMULATE);
     k_wf_accumulate<<<(pixels + WF_BLOCK - 1) / WF_BLOCK, WF_BLOCK, 0, st>>>(L, B, dOut, pixels, frame0, nf, P.cls);
+    mark(1, st, LT_TIMED_ACCUMULATE);
     if (overlap) cudaEventRecord(aux->order[side], st);
     lastSide = side;
     launches++;

@@ -110,10 +110,12 @@ def test_bounce_caps_beyond_the_wavefront_depth_field(ctx):
     got = ctx.render(sc, cam, capi.make_params(L.KERNEL_GI, w, h, max_ray_depth=40))
     assert_images_match(got, want, "max_ray_depth 40, default schedule", max_outliers=3)
     # enough paths for the wavefront to be the default choice: still correct (falls back to the megakernel)
+    ctx.accum_reset()
     big = ctx.render(sc, cam, capi.make_params(L.KERNEL_GI, 1920, 1080, max_ray_depth=33, frames=5,
-                                               accum_mode=L.ACCUM_RUNNING_MEAN, flags=0))
+                                               accum_mode=L.ACCUM_RUNNING_MEAN, flags=0)).copy()
+    ctx.accum_reset()
     mega = ctx.render(sc, cam, capi.make_params(L.KERNEL_GI, 1920, 1080, max_ray_depth=33, frames=5,
-                                                accum_mode=L.ACCUM_RUNNING_MEAN, flags=L.FLAG_MEGAKERNEL))
+                                                accum_mode=L.ACCUM_RUNNING_MEAN, flags=L.FLAG_MEGAKERNEL)).copy()
     util.assert_bit_equal(big, mega, "depth 33: default schedule vs megakernel")
     with pytest.raises(capi.LtError):
         ctx.render(sc, cam, capi.make_params(L.KERNEL_GI, w, h, max_ray_depth=33, flags=L.FLAG_WAVEFRONT))
@@ -163,7 +165,10 @@ def test_unreachable_nodes_are_rejected(ctx):
 # ---------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", ["green_wall", "cornell_box", "cornell_box_lens"])
 @pytest.mark.parametrize("size", [(1920, 1080), (257, 130), (7, 3), (1, 1)])
-def test_streamed_flat_kernel_equals_one_thread_per_pixel(ctx, name, size):
+def test_streamed_flat_kernel_equals_one_thread_per_pixel(ctx, name, size, monkeypatch):
+    """k_flat_stream (persistent warps that fetch 8x4 tiles; the default on large scenes, forced here on the small
+    ones through LT_STREAM_MIN_NODES=0) == k_flat == the oracle, including the lens path and the frame combiner."""
+    monkeypatch.setenv("LT_STREAM_MIN_NODES", "0")
     sb = util.scene(name)
     sc = ctx.upload(sb)
     w, h = size
@@ -185,30 +190,6 @@ def test_streamed_flat_kernel_equals_one_thread_per_pixel(ctx, name, size):
     sc.release()
 
 
-@pytest.mark.parametrize("kernel,depth,frames", [(L.KERNEL_ACCUMULATOR, 0, 1), (L.KERNEL_GI, 4, 3), (L.KERNEL_GI25, 2, 1),
-                                                 (L.KERNEL_LIGHTING25, 0, 2)])
-def test_megakernel_with_dealt_pixels_equals_fixed_pixels(ctx, kernel, depth, frames):
-    """k_path takes the next pixel from a global counter when a lane's pixel is done (the default on large
-    scenes; forced here on the small ones through LT_PATH_DYNAMIC=1): same image as one pixel per thread."""
-    for name in ("cornell_box", "cornell_box_lens"):
-        sb = util.scene(name)
-        sc = ctx.upload(sb)
-        cam = util.default_camera(0.02, 2)
-        for w, h in ((200, 150), (33, 17)):
-            p = dict(max_ray_depth=depth, frames=frames, accum_mode=L.ACCUM_RUNNING_MEAN)
-            ctx.accum_reset()
-            fixed = ctx.render(sc, cam, capi.make_params(kernel, w, h, flags=L.FLAG_MEGAKERNEL | L.FLAG_NO_STREAM, **p)).copy()
-            os.environ["LT_PATH_DYNAMIC"] = "1"
-            try:
-                for extra in (0, L.FLAG_NO_THREADED):
-                    ctx.accum_reset()
-                    dealt = ctx.render(sc, cam, capi.make_params(kernel, w, h, flags=L.FLAG_MEGAKERNEL | extra, **p)).copy()
-                    util.assert_bit_equal(dealt, fixed, "%s kernel %d %dx%d dealt vs fixed pixels" % (name, kernel, w, h))
-            finally:
-                os.environ.pop("LT_PATH_DYNAMIC")
-        sc.release()
-
-
 # ---------------------------------------------------------------------------------------------------------------
 # BASELINE.json configurations at their full sizes
 # ---------------------------------------------------------------------------------------------------------------
@@ -223,7 +204,7 @@ def test_synth1m_primary_hits_full_frame_bit_exact(ctx, synth1m):
     np.testing.assert_array_equal(hit, ohit)
     np.testing.assert_array_equal(ids, oids)
     util.assert_bit_equal(tuv, otuv, "1 M triangles: t,u,v at 1080p")
-    assert len(np.unique(ids)) > 100000  # the frame really sees the mesh
+    assert len(np.unique(ids)) > 50000  # the frame really sees the mesh
     want = O.render(L.KERNEL_BASIC_CU, sb, cam, w, h)
     for flags in (0, L.FLAG_NO_STREAM, L.FLAG_CULL):
         got = ctx.render(sc, cam, capi.make_params(L.KERNEL_BASIC_CU, w, h, flags=flags))
@@ -238,15 +219,15 @@ def test_synth1m_shadow_and_gi_all_schedules(ctx, synth1m):
     cam = util.default_camera(0.0, 0)
     want = O.render(L.KERNEL_ACCUMULATOR, sb, cam, w, h, threads=0)
     imgs = []
-    for flags in (0, L.FLAG_MEGAKERNEL | L.FLAG_NO_STREAM, L.FLAG_WAVEFRONT):
+    for flags in (0, L.FLAG_MEGAKERNEL, L.FLAG_WAVEFRONT):
         got = ctx.render(sc, cam, capi.make_params(L.KERNEL_ACCUMULATOR, w, h, flags=flags)).copy()
         assert_images_match(got, want, "1 M triangles: primary + shadow, flags %d" % flags, max_outliers=8)
         imgs.append(got)
-    util.assert_bit_equal(imgs[0], imgs[1], "dealt pixels vs fixed pixels")
+    util.assert_bit_equal(imgs[0], imgs[1], "default vs megakernel")
     util.assert_bit_equal(imgs[0], imgs[2], "megakernel vs wavefront")
     cam = util.default_camera(0.0, 5)
     gi = [ctx.render(sc, cam, capi.make_params(L.KERNEL_GI, w, h, max_ray_depth=4, flags=f)).copy()
-          for f in (0, L.FLAG_MEGAKERNEL | L.FLAG_NO_STREAM, L.FLAG_WAVEFRONT, L.FLAG_WAVEFRONT | L.FLAG_SERIAL)]
+          for f in (0, L.FLAG_MEGAKERNEL, L.FLAG_WAVEFRONT, L.FLAG_WAVEFRONT | L.FLAG_SERIAL)]
     for k in range(1, 4):
         util.assert_bit_equal(gi[0], gi[k], "GI on 1 M triangles: schedule %d vs default" % k)
     for rows in ((0, 8), (536, 552), (1072, 1080)):

@@ -18,7 +18,7 @@ def test_libraries_export_every_declared_symbol():
     hl = host.load()
     for name in host.SYMBOLS:
         assert hasattr(hl, name), name
-    assert lib.lt_api_version() == 1
+    assert lib.lt_api_version() == 2
     # every function the header declares is bound above
     header = open(os.path.join(util.ROOT, "include", "lens_trace_b200.h")).read()
     import re
