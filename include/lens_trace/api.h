@@ -132,6 +132,9 @@ struct RenderExtensionB200 {
   uint64_t nodeTests;      // out
   uint64_t triTests;       // out
   float kernelMilliseconds;  // out: device time of the render kernels
+  // --- multi-GPU (appended: older initialisers leave them 0 = one GPU) ---
+  uint32_t deviceCount;    // GPUs 0 .. deviceCount-1 of this process render the call together (0, 1: device 0 only)
+  uint32_t splitMode;      // 0 auto, 1 samples (one NCCL all-reduce per call), 2 tiles (blocks of 8 rows, no collective)
 };
 
 // ================================================================================================
@@ -426,10 +429,13 @@ private:
     uint64_t checksum;
     uint64_t lastUse;
     lt_scene* scene;
+    lt_scene* groupScene;  // the same scene replicated on the devices of groupCtx, when it was rendered there
   };
   static const size_t kMaxScenes = 8;
   lt_ctx* ctx;
   std::vector<CachedScene> sceneCache;
+  lt_ctx* groupCtx;      // multi-GPU context (lt_ctx_create_multi), made on first use of RenderExtensionB200::deviceCount
+  uint32_t groupDevices;
   uint64_t useCounter;
   uint64_t seenRetireGeneration;
   std::map<std::string, int> kernelCache;
@@ -497,7 +503,7 @@ public:
 // scene_parser.h -- JSON .scene file -> Camera / Model / AccelerationStructureExplicit / RenderProperties*
 // (reference: include/lens_trace/scene_parser.h, src/scene_parser.cpp; same keys, same defaults).
 // The JSON reader is this project's own (lens_trace_b200/host/scene_parser.cpp).  B200 additions,
-// all optional, under "renderer": "frames", "accumulate", "max_ray_depth".
+// all optional, under "renderer": "frames", "accumulate", "max_ray_depth", "devices", "split".
 // ================================================================================================
 struct RendererParsed {
   RenderPlatform renderPlatform = RENDER_PLATFORM_OPENCL;
@@ -512,6 +518,8 @@ struct RendererParsed {
   uint32_t frames = 1;        // B200
   uint32_t accumulate = 0;    // B200
   uint32_t maxRayDepth = 0;   // B200 (0 -> 16)
+  uint32_t deviceCount = 0;   // B200: "devices" (GPUs 0..n-1 render each call together)
+  uint32_t splitMode = 0;     // B200: "split": "samples" | "tiles" (default: chosen per call)
 };
 
 struct CameraParsed {

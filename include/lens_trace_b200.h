@@ -75,6 +75,15 @@ enum lt_flags {
                                   output, kept selectable so tests can compare the two) */
 };
 
+/* How a multi-GPU context (lt_ctx_create_multi) divides one lt_render call among its devices. */
+enum lt_split_mode {
+  LT_SPLIT_AUTO = 0,    /* samples when the call accumulates two or more frames, tiles otherwise */
+  LT_SPLIT_SAMPLES = 1, /* device g renders frames g, g+G, ...; the per-device accumulators are combined by one
+                           all-reduce (NCCL over NVLink) per call */
+  LT_SPLIT_TILES = 2    /* device g renders every G-th block of 8 image rows; no collective, every device copies
+                           its rows to the host buffer */
+};
+
 typedef struct lt_ctx lt_ctx;
 typedef struct lt_scene lt_scene;
 
@@ -93,6 +102,8 @@ typedef struct lt_render_params {
   int32_t flags;          /* enum lt_flags */
   int32_t block_x;        /* thread-block shape hint (ThreadOrganizationCUDA.blockSize); 0 = library default. */
   int32_t block_y;        /* Output never depends on it (tests/cuda_renderer_test.cc:51-115). */
+  int32_t split_mode;     /* API version 2, multi-GPU contexts only: one of enum lt_split_mode; a struct_size without this
+                             field is accepted and means LT_SPLIT_AUTO */
 } lt_render_params;
 
 typedef struct lt_stats {
@@ -116,6 +127,12 @@ typedef struct lt_stats {
 
 /* --- context: replaces RendererCUDA::RendererCUDA() (src/cuda/renderer_cuda.cpp:10-14). --- */
 int lt_ctx_create(int device_ordinal, lt_ctx** out_ctx);
+/* Multi-GPU context on the given devices of this process (the reference renders on device 0
+ * only, src/cuda/renderer_cuda.cpp:12).  lt_scene_upload replicates the scene on every device, lt_render divides the
+ * call by params->split_mode and returns the combined frame in host_out.  device_count == 1 behaves like
+ * lt_ctx_create.  The sample split needs NCCL (libnccl.so.2, loaded on first use). */
+int lt_ctx_create_multi(const int* device_ordinals, int device_count, lt_ctx** out_ctx);
+int lt_ctx_device_count(const lt_ctx* ctx);
 void lt_ctx_destroy(lt_ctx* ctx);
 /* Last error message of ctx (or of the failed lt_ctx_create when ctx == NULL). Never NULL. */
 const char* lt_last_error(const lt_ctx* ctx);

@@ -18,7 +18,7 @@ SYMBOLS = [
     "lt_api_version", "lt_ctx_create", "lt_ctx_destroy", "lt_last_error", "lt_ctx_set_stream", "lt_scene_upload",
     "lt_scene_release", "lt_render", "lt_render_device", "lt_accum_reset", "lt_accum_read", "lt_primary_hits",
     "lt_last_stats", "lt_kernel_from_path", "lt_kernel_name", "lt_debug_random", "lt_debug_hemisphere", "lt_debug_build_threaded", "lt_plugin_load", "lt_render_plugin", "lt_primary_hits_flags", "lt_scene_build_lbvh", "lt_scene_download", "lt_scene_info",
-    "lt_debug_gather_peak",
+    "lt_debug_gather_peak", "lt_ctx_create_multi", "lt_ctx_device_count",
 ]
 
 
@@ -31,7 +31,7 @@ class RenderParams(C.Structure):
         ("struct_size", C.c_uint32), ("kernel", C.c_int32), ("kernel_mode", C.c_int32), ("width", C.c_int32),
         ("height", C.c_int32), ("depth", C.c_int32), ("max_ray_depth", C.c_int32), ("frames", C.c_int32),
         ("frame_stride", C.c_uint32), ("accum_mode", C.c_int32), ("accum_weight", C.c_float), ("flags", C.c_int32),
-        ("block_x", C.c_int32), ("block_y", C.c_int32),
+        ("block_x", C.c_int32), ("block_y", C.c_int32), ("split_mode", C.c_int32),
     ]
 
 
@@ -57,6 +57,8 @@ def load():
     lib = C.CDLL(LIB_PATH)
     lib.lt_api_version.restype = C.c_int
     lib.lt_ctx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    lib.lt_ctx_create_multi.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]
+    lib.lt_ctx_device_count.argtypes = [C.c_void_p]
     lib.lt_ctx_destroy.argtypes = [C.c_void_p]
     lib.lt_ctx_destroy.restype = None
     lib.lt_last_error.argtypes = [C.c_void_p]
@@ -98,26 +100,34 @@ def kernel_from_path(path):
 
 
 def make_params(kernel, width, height, depth=3, kernel_mode=0, max_ray_depth=0, frames=1, frame_stride=1,
-                accum_mode=L.ACCUM_NONE, accum_weight=0.0, flags=0):
+                accum_mode=L.ACCUM_NONE, accum_weight=0.0, flags=0, split_mode=0):
     p = RenderParams()
     p.struct_size = C.sizeof(RenderParams)
     p.kernel, p.kernel_mode = kernel, kernel_mode
     p.width, p.height, p.depth = width, height, depth
     p.max_ray_depth, p.frames, p.frame_stride = max_ray_depth, frames, frame_stride
     p.accum_mode, p.accum_weight, p.flags = accum_mode, accum_weight, flags
+    p.split_mode = split_mode
     return p
 
 
 class Context:
-    """lt_ctx: one per GPU."""
+    """lt_ctx: one per GPU, or -- device = a list of ordinals -- one multi-GPU context (lt_ctx_create_multi)."""
 
     def __init__(self, device=0):
         self.lib = load()
         h = C.c_void_p()
-        rc = self.lib.lt_ctx_create(device, C.byref(h))
+        if isinstance(device, (list, tuple)):
+            arr = (C.c_int * len(device))(*device)
+            rc = self.lib.lt_ctx_create_multi(arr, len(device), C.byref(h))
+        else:
+            rc = self.lib.lt_ctx_create(device, C.byref(h))
         if rc != 0:
             raise LtError("lt_ctx_create failed (%d): %s" % (rc, self.lib.lt_last_error(None).decode()))
         self.h = h
+
+    def device_count(self):
+        return self.lib.lt_ctx_device_count(self.h)
 
     def close(self):
         if self.h:

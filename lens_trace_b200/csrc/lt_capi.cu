@@ -4,44 +4,13 @@
 #include "lens_trace_b200.h"
 #include "lt_internal.h"
 
+#include <stddef.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
 #include <string>
 #include <vector>
-
-struct lt_ctx {
-  int device = 0;
-  cudaStream_t ownStream = nullptr;
-  cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  std::string error;
-  float* dOut = nullptr;  // context-owned output / accumulator
-  size_t outFloats = 0;
-  LtCounters* dCounters = nullptr;
-  int* dWork = nullptr;  // work counters of the persistent kernels
-  std::vector<cudaEvent_t> traceEvents;  // pairs of events around launches (timed when synchronous)
-  std::vector<unsigned char> pairKinds;  // LT_TIMED_* of every pair
-  std::vector<LtPlugin*> plugins;  // compiled user kernels, by id
-  RefCamera* dCamera = nullptr;    // camera buffer for plug-in launches
-  void* wfWorkspace = nullptr;  // wavefront path state / ray queues (two batch workspaces when batches overlap)
-  size_t wfBytes = 0;
-  LtWfAux wfAux = {};           // second stream + events for overlapping consecutive wavefront batches
-  size_t totalMem = 0;
-  lt_stats stats = {};
-};
-
-struct lt_scene {
-  RefNode* dNodes = nullptr;
-  RefPrim* dPrims = nullptr;
-  RefMaterial* dMats = nullptr;
-  RefLights* dLights = nullptr;
-  LtWideNode* dWide = nullptr;
-  LtTri* dTris = nullptr;
-  LtThreadNode* dThread = nullptr;  // 8 octant copies in visit order, small scenes only
-  LtSceneDev dev = {};
-};
 
 static thread_local std::string g_error = "";
 
@@ -50,6 +19,7 @@ static int fail(lt_ctx* ctx, int code, const std::string& msg) {
   g_error = msg;
   return code;
 }
+int lt_internal_fail(lt_ctx* ctx, int code, const std::string& msg) { return fail(ctx, code, msg); }
 
 #define CK(call)                                                                                     \
   do {                                                                                               \
@@ -109,6 +79,11 @@ extern "C" int lt_ctx_create(int device_ordinal, lt_ctx** out_ctx) {
 
 extern "C" void lt_ctx_destroy(lt_ctx* ctx) {
   if (!ctx) return;
+  if (ctx->group) {
+    lt_multi_destroy(ctx);
+    delete ctx;
+    return;
+  }
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->dOut) cudaFree(ctx->dOut);
@@ -134,6 +109,7 @@ extern "C" void lt_ctx_destroy(lt_ctx* ctx) {
 
 extern "C" int lt_ctx_set_stream(lt_ctx* ctx, void* cuda_stream) {
   if (!ctx) return fail(nullptr, LT_ERR_INVALID, "lt_ctx_set_stream: ctx is NULL");
+  if (ctx->group) return fail(ctx, LT_ERR_UNSUPPORTED, "lt_ctx_set_stream: a multi-GPU context renders on its own per-device streams");
   ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->ownStream;
   return LT_OK;
 }
@@ -174,6 +150,10 @@ static int validate_tree(const RefNode* nodes, int nodeCount, int primCount, int
 
 extern "C" void lt_scene_release(lt_ctx* ctx, lt_scene* s) {
   if (!s) return;
+  if (!s->parts.empty()) {
+    lt_multi_scene_release(ctx, s);
+    return;
+  }
   if (ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
@@ -322,6 +302,7 @@ static int finish_scene(lt_ctx* ctx, lt_scene* s, int nNodes, int nPrims, int nM
 extern "C" int lt_scene_build_lbvh(lt_ctx* ctx, const void* primitives, uint64_t primitive_bytes, const void* materials,
                                    uint64_t material_bytes, lt_scene** out_scene) {
   if (!ctx) return fail(nullptr, LT_ERR_INVALID, "lt_scene_build_lbvh: ctx is NULL");
+  if (ctx->group) return fail(ctx, LT_ERR_UNSUPPORTED, "lt_scene_build_lbvh: build on a single-GPU context, download, and upload to the multi-GPU context");
   if (!out_scene || !primitives || !materials) return fail(ctx, LT_ERR_INVALID, "lt_scene_build_lbvh: NULL argument");
   *out_scene = nullptr;
   if (primitive_bytes == 0 || primitive_bytes % sizeof(RefPrim) || material_bytes == 0 ||
@@ -378,6 +359,7 @@ extern "C" int lt_scene_build_lbvh(lt_ctx* ctx, const void* primitives, uint64_t
 extern "C" int lt_scene_download(lt_ctx* ctx, lt_scene* scene, void* nodes, uint64_t node_bytes, void* primitives,
                                  uint64_t primitive_bytes, void* light_container) {
   if (!ctx || !scene) return fail(ctx, LT_ERR_INVALID, "lt_scene_download: NULL argument");
+  if (ctx->group) return fail(ctx, LT_ERR_UNSUPPORTED, "lt_scene_download: not available on a multi-GPU context");
   CK(cudaSetDevice(ctx->device));
   CK(cudaStreamSynchronize(ctx->stream));
   if (nodes) {
@@ -394,6 +376,7 @@ extern "C" int lt_scene_download(lt_ctx* ctx, lt_scene* scene, void* nodes, uint
 
 extern "C" int lt_scene_info(const lt_scene* scene, uint64_t* node_count, uint64_t* primitive_count, int32_t* stack_depth) {
   if (!scene) return LT_ERR_INVALID;
+  if (!scene->parts.empty()) scene = scene->parts[0];
   if (node_count) *node_count = (uint64_t)scene->dev.nodeCount;
   if (primitive_count) *primitive_count = (uint64_t)scene->dev.primCount;
   if (stack_depth) *stack_depth = scene->dev.stackDepth;
@@ -405,6 +388,9 @@ extern "C" int lt_scene_upload(lt_ctx* ctx, const void* nodes, uint64_t node_byt
                                const void* light_container, uint64_t light_bytes, lt_scene** out_scene) {
   if (!ctx) return fail(nullptr, LT_ERR_INVALID, "lt_scene_upload: ctx is NULL");
   if (!out_scene) return fail(ctx, LT_ERR_INVALID, "lt_scene_upload: out_scene is NULL");
+  if (ctx->group)
+    return lt_multi_scene_upload(ctx, nodes, node_bytes, primitives, primitive_bytes, materials, material_bytes,
+                                 light_container, light_bytes, out_scene);
   *out_scene = nullptr;
   if (!nodes || !primitives || !materials || !light_container)
     return fail(ctx, LT_ERR_INVALID, "lt_scene_upload: NULL buffer");
@@ -461,7 +447,8 @@ static int check_params(lt_ctx* ctx, const lt_scene* scene, const void* camera28
                         LtLaunch* L) {
   if (!ctx) return fail(nullptr, LT_ERR_INVALID, "lt_render: ctx is NULL");
   if (!scene || !camera28 || !p) return fail(ctx, LT_ERR_INVALID, "lt_render: NULL argument");
-  if (p->struct_size != sizeof(lt_render_params))
+  // API version 1 callers pass the struct without its last field (split_mode)
+  if (p->struct_size != sizeof(lt_render_params) && p->struct_size != offsetof(lt_render_params, split_mode))
     return fail(ctx, LT_ERR_INVALID, "lt_render: params.struct_size mismatch");
   if (p->kernel < 0 || p->kernel >= LT_KERNEL_COUNT) return fail(ctx, LT_ERR_UNSUPPORTED, "lt_render: unknown kernel id");
   if (p->width <= 0 || p->height <= 0 || p->depth < 3)
@@ -475,6 +462,10 @@ static int check_params(lt_ctx* ctx, const lt_scene* scene, const void* camera28
   L->kernelMode = p->kernel_mode ? 1 : 0;
   L->width = p->width;
   L->height = p->height;
+  L->fullHeight = p->height;
+  L->rowBlock = p->height;
+  L->rowStride = 1;
+  L->rowPhase = 0;
   L->depth = p->depth;
   L->maxRayDepth = p->max_ray_depth;
   L->frames = p->frames;
@@ -519,7 +510,9 @@ static int check_params(lt_ctx* ctx, const lt_scene* scene, const void* camera28
   return LT_OK;
 }
 
-static int ensure_out(lt_ctx* ctx, size_t floats) {
+int lt_internal_ensure_out(lt_ctx* ctx, size_t floats);
+static int ensure_out(lt_ctx* ctx, size_t floats) { return lt_internal_ensure_out(ctx, floats); }
+int lt_internal_ensure_out(lt_ctx* ctx, size_t floats) {
   if (ctx->outFloats >= floats) return LT_OK;
   if (ctx->dOut) cudaFree(ctx->dOut);
   ctx->dOut = nullptr;
@@ -675,6 +668,8 @@ static int render_common(lt_ctx* ctx, lt_scene* scene, const LtLaunch& L, float*
 
 extern "C" int lt_render_device(lt_ctx* ctx, lt_scene* scene, const void* camera28, const lt_render_params* params,
                                 float* device_out, int sync) {
+  if (ctx && ctx->group)
+    return fail(ctx, LT_ERR_UNSUPPORTED, "lt_render_device: a multi-GPU context renders into host memory (lt_render)");
   LtLaunch L;
   int rc = check_params(ctx, scene, camera28, params, &L);
   if (rc != LT_OK) return rc;
@@ -682,8 +677,21 @@ extern "C" int lt_render_device(lt_ctx* ctx, lt_scene* scene, const void* camera
   return render_common(ctx, scene, L, device_out, sync != 0);
 }
 
+int lt_internal_render_rows(lt_ctx* ctx, lt_scene* scene, const void* camera28, const lt_render_params* params,
+                            float* device_out, int fullHeight, int rowBlock, int rowStride, int rowPhase, int sync) {
+  LtLaunch L;
+  int rc = check_params(ctx, scene, camera28, params, &L);
+  if (rc != LT_OK) return rc;
+  L.fullHeight = fullHeight;
+  L.rowBlock = rowBlock;
+  L.rowStride = rowStride;
+  L.rowPhase = rowPhase;
+  return render_common(ctx, scene, L, device_out, sync != 0);
+}
+
 extern "C" int lt_render(lt_ctx* ctx, lt_scene* scene, const void* camera28, const lt_render_params* params,
                          float* host_out) {
+  if (ctx && ctx->group) return lt_multi_render(ctx, scene, camera28, params, host_out);
   LtLaunch L;
   int rc = check_params(ctx, scene, camera28, params, &L);
   if (rc != LT_OK) return rc;
@@ -699,6 +707,7 @@ extern "C" int lt_render(lt_ctx* ctx, lt_scene* scene, const void* camera28, con
 
 extern "C" int lt_plugin_load(lt_ctx* ctx, const char* kernel_file_path, int* out_plugin_id) {
   if (!ctx || !kernel_file_path || !out_plugin_id) return fail(ctx, LT_ERR_INVALID, "lt_plugin_load: NULL argument");
+  if (ctx->group) return fail(ctx, LT_ERR_UNSUPPORTED, "lt_plugin_load: plug-in kernels run on single-GPU contexts");
   CK(cudaSetDevice(ctx->device));
   CK(cudaFree(0));  // make sure the primary context is current for the driver-API module load
   std::string err;
@@ -712,6 +721,7 @@ extern "C" int lt_plugin_load(lt_ctx* ctx, const char* kernel_file_path, int* ou
 extern "C" int lt_render_plugin(lt_ctx* ctx, lt_scene* scene, const void* camera28, int plugin_id, int kernel_mode,
                                 int width, int height, int depth, int block_x, int block_y, float* host_out) {
   if (!ctx) return fail(nullptr, LT_ERR_INVALID, "lt_render_plugin: ctx is NULL");
+  if (ctx->group) return fail(ctx, LT_ERR_UNSUPPORTED, "lt_render_plugin: plug-in kernels run on single-GPU contexts");
   if (!scene || !camera28 || plugin_id < 0 || plugin_id >= (int)ctx->plugins.size() || width <= 0 || height <= 0 ||
       depth < 1)
     return fail(ctx, LT_ERR_INVALID, "lt_render_plugin: bad argument");
@@ -737,6 +747,7 @@ extern "C" int lt_render_plugin(lt_ctx* ctx, lt_scene* scene, const void* camera
 
 extern "C" int lt_accum_reset(lt_ctx* ctx) {
   if (!ctx) return fail(nullptr, LT_ERR_INVALID, "lt_accum_reset: ctx is NULL");
+  if (ctx->group) return lt_multi_accum_reset(ctx);
   CK(cudaSetDevice(ctx->device));
   if (ctx->dOut) CK(cudaMemsetAsync(ctx->dOut, 0, ctx->outFloats * sizeof(float), ctx->stream));
   return LT_OK;
@@ -744,6 +755,7 @@ extern "C" int lt_accum_reset(lt_ctx* ctx) {
 
 extern "C" int lt_accum_read(lt_ctx* ctx, float* host_out, uint64_t float_count) {
   if (!ctx || !host_out) return fail(ctx, LT_ERR_INVALID, "lt_accum_read: NULL argument");
+  if (ctx->group) return fail(ctx, LT_ERR_UNSUPPORTED, "lt_accum_read: a multi-GPU context returns its accumulator through lt_render");
   if (!ctx->dOut || float_count > ctx->outFloats) return fail(ctx, LT_ERR_INVALID, "lt_accum_read: no accumulator of that size");
   CK(cudaSetDevice(ctx->device));
   CK(cudaStreamSynchronize(ctx->stream));
@@ -767,6 +779,7 @@ extern "C" int lt_primary_hits_flags(lt_ctx* ctx, lt_scene* scene, const void* c
 static int primary_hits_impl(lt_ctx* ctx, lt_scene* scene, const void* camera28, int kernel, int flags, int width,
                              int height, int32_t* ids, int32_t* hit, float* tuv) {
   if (!ctx) return fail(nullptr, LT_ERR_INVALID, "lt_primary_hits: ctx is NULL");
+  if (ctx->group) return fail(ctx, LT_ERR_UNSUPPORTED, "lt_primary_hits: use a single-GPU context");
   if (!scene || !camera28 || width <= 0 || height <= 0 || kernel < 0 || kernel >= LT_KERNEL_COUNT)
     return fail(ctx, LT_ERR_INVALID, "lt_primary_hits: bad argument");
   CK(cudaSetDevice(ctx->device));
@@ -790,7 +803,7 @@ static int primary_hits_impl(lt_ctx* ctx, lt_scene* scene, const void* camera28,
 
 // parity hooks: evaluate device-side helper functions on host-supplied inputs
 extern "C" int lt_debug_random(lt_ctx* ctx, const float* fx, const float* fy, const float* seed, int n, float* out) {
-  if (!ctx || !fx || !fy || !seed || !out || n <= 0) return fail(ctx, LT_ERR_INVALID, "lt_debug_random: bad argument");
+  if (!ctx || ctx->group || !fx || !fy || !seed || !out || n <= 0) return fail(ctx, LT_ERR_INVALID, "lt_debug_random: bad argument");
   CK(cudaSetDevice(ctx->device));
   float* d = nullptr;
   CK(cudaMalloc(&d, sizeof(float) * 4 * (size_t)n));
@@ -806,7 +819,7 @@ extern "C" int lt_debug_random(lt_ctx* ctx, const float* fx, const float* fy, co
 }
 
 extern "C" int lt_debug_hemisphere(lt_ctx* ctx, const float* u1, const float* u2, const float* up3, int n, float* out4) {
-  if (!ctx || !u1 || !u2 || !up3 || !out4 || n <= 0) return fail(ctx, LT_ERR_INVALID, "lt_debug_hemisphere: bad argument");
+  if (!ctx || ctx->group || !u1 || !u2 || !up3 || !out4 || n <= 0) return fail(ctx, LT_ERR_INVALID, "lt_debug_hemisphere: bad argument");
   CK(cudaSetDevice(ctx->device));
   float* d = nullptr;
   CK(cudaMalloc(&d, sizeof(float) * 9 * (size_t)n));

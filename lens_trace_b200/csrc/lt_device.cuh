@@ -635,6 +635,13 @@ __host__ __device__ inline float lt_eps(int kernel) {
 }
 
 // camera ray, basic.cu:350-358; fused forms as NVRTC+ptxas emit them (oracle/notes_fma_order.md)
+// image row of local row j of this launch (identity unless the launch is one device's share of a tile split)
+__device__ __forceinline__ int lt_image_row(const LtLaunch& L, int j) {
+  if (L.rowStride <= 1) return j;
+  const int b = j / L.rowBlock;
+  return (b * L.rowStride + L.rowPhase) * L.rowBlock + (j - b * L.rowBlock);
+}
+
 // c, s = cosf(cam.yaw), sinf(cam.yaw): the same for every pixel, so persistent kernels evaluate them once
 __device__ __forceinline__ Ray camera_ray_cs(const RefCamera& cam, float c, float s, int px, int py, int width,
                                              int height, float& fx, float& fy) {

@@ -21,6 +21,10 @@ struct LtLaunch {
   int batchClosest;     // k_path: leaves recorded before a closest-hit ray tests them
   int iterNodeSteps;    // trav_iter: box-pair tests per iteration of a persistent loop
   int iterTriTests;     // trav_iter: triangle tests per iteration
+  // Row window of a tile split (multi-GPU): this launch renders `height` rows of an image of `fullHeight` rows;
+  // local row j is image row ((j / rowBlock) * rowStride + rowPhase) * rowBlock + j % rowBlock (blocks of rowBlock
+  // rows dealt round-robin to rowStride devices).  rowStride <= 1: the whole image (fullHeight == height).
+  int fullHeight, rowBlock, rowStride, rowPhase;
   RefCamera cam;
 };
 
@@ -77,6 +81,60 @@ void lt_plugin_free(LtPlugin* p);
 int lt_plugin_launch(LtPlugin* p, int kernelMode, const LtSceneDev* sceneDev, const void* dNodes, const void* dPrims,
                      const void* dMats, const void* dLights, const void* dCamera, float* dOut, int width, int height,
                      int depth, int bx, int by, cudaStream_t stream, std::string* err);
+
+// ---- context and scene objects behind the C-ABI handles (lt_capi.cu; lt_multi.cu for multi-GPU contexts) ----
+#include <vector>
+#include "lens_trace_b200.h"
+struct LtGroup;  // lt_multi.cu: the devices of a multi-GPU context
+
+struct lt_ctx {
+  int device = 0;
+  LtGroup* group = nullptr;  // non-NULL: a multi-GPU context (lt_ctx_create_multi); the fields below are unused
+  cudaStream_t ownStream = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string error;
+  float* dOut = nullptr;  // context-owned output / accumulator
+  size_t outFloats = 0;
+  LtCounters* dCounters = nullptr;
+  int* dWork = nullptr;  // work counters of the persistent kernels
+  std::vector<cudaEvent_t> traceEvents;  // pairs of events around launches (timed when synchronous)
+  std::vector<unsigned char> pairKinds;  // LT_TIMED_* of every pair
+  std::vector<LtPlugin*> plugins;  // compiled user kernels, by id
+  RefCamera* dCamera = nullptr;    // camera buffer for plug-in launches
+  void* wfWorkspace = nullptr;  // wavefront path state / ray queues (two batch workspaces when batches overlap)
+  size_t wfBytes = 0;
+  LtWfAux wfAux = {};           // second stream + events for overlapping consecutive wavefront batches
+  size_t totalMem = 0;
+  lt_stats stats = {};
+};
+
+struct lt_scene {
+  std::vector<lt_scene*> parts;  // scene of a multi-GPU context: one uploaded copy per device (then nothing else is set)
+  RefNode* dNodes = nullptr;
+  RefPrim* dPrims = nullptr;
+  RefMaterial* dMats = nullptr;
+  RefLights* dLights = nullptr;
+  LtWideNode* dWide = nullptr;
+  LtTri* dTris = nullptr;
+  LtThreadNode* dThread = nullptr;  // 8 octant copies in visit order, small scenes only
+  LtSceneDev dev = {};
+};
+
+
+// multi-GPU contexts (lt_multi.cu); every entry point of lt_capi.cu forwards to these when ctx->group is set
+int lt_multi_scene_upload(lt_ctx* ctx, const void* nodes, uint64_t node_bytes, const void* primitives,
+                          uint64_t primitive_bytes, const void* materials, uint64_t material_bytes,
+                          const void* light_container, uint64_t light_bytes, lt_scene** out_scene);
+void lt_multi_scene_release(lt_ctx* ctx, lt_scene* scene);
+int lt_multi_render(lt_ctx* ctx, lt_scene* scene, const void* camera28, const lt_render_params* params, float* host_out);
+void lt_multi_destroy(lt_ctx* ctx);
+int lt_multi_accum_reset(lt_ctx* ctx);
+int lt_internal_fail(lt_ctx* ctx, int code, const std::string& msg);  // sets the context's (and the thread's) last error
+int lt_internal_ensure_out(lt_ctx* ctx, size_t floats);
+// one device's share of a render call: like lt_render_device, with the row window of a tile split
+int lt_internal_render_rows(lt_ctx* ctx, lt_scene* scene, const void* camera28, const lt_render_params* params,
+                            float* device_out, int fullHeight, int rowBlock, int rowStride, int rowPhase, int sync);
 
 // device-side LBVH construction in the reference's flattened layout (lt_bvh.cu)
 size_t lt_bvh_scratch_bytes(int n);

@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(LT_BLOCK) k_flat(LtSceneDev sc, LtLaunch L, fl
   LtCounters cnt = {0, 0, 0};
   float fx, fy;
   Trav t;
-  t.r = camera_ray(L.cam, px, py, L.width, L.height, fx, fy);
+  t.r = camera_ray(L.cam, px, lt_image_row(L, py), L.width, L.fullHeight, fx, fy);
   const float tInit = lt_tinit(L.kernel), epsThr = lt_eps(L.kernel);
   float color[3] = {0.0f, 0.0f, 0.0f};
   const bool cull = (L.flags & 2) != 0;  // LT_FLAG_CULL
@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(LT_BLOCK) k_flat_stream(LtSceneDev sc, LtLaunc
     if (px >= L.width || py >= L.height) continue;  // (the other lanes of the warp run their pixels; no barrier follows)
     float fx, fy;
     Trav t;
-    t.r = camera_ray_cs(L.cam, camC, camS, px, py, L.width, L.height, fx, fy);
+    t.r = camera_ray_cs(L.cam, camC, camS, px, lt_image_row(L, py), L.width, L.fullHeight, fx, fy);
     float color[3] = {0.0f, 0.0f, 0.0f};
     int baseMat = 0;  // material of the camera ray's hit (kept when the lens path ends in a miss)
     float r2w = 0.0f;
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(LT_BLOCK) k_path(LtSceneDev sc, LtLaunch L, fl
   FrameSink sink;
   sink.acc[0] = sink.acc[1] = sink.acc[2] = 0.0f;
   if (alive) {
-    cameraRay = camera_ray(L.cam, px, py, L.width, L.height, fx, fy);
+    cameraRay = camera_ray(L.cam, px, lt_image_row(L, py), L.width, L.fullHeight, fx, fy);
     id = ((long long)py * L.width + px) * L.depth;
     sink.begin(L, out, id);
   }

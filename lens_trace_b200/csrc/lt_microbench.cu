@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(128) k_mb_gather(const LtGatherRec* __restrict
 
 extern "C" int lt_debug_gather_peak(lt_ctx* ctx, uint64_t table_bytes, int dependent, int ilp, int blocks_per_sm,
                                     int iters, double* out_gbs, double* out_ns_per_load) {
-  if (!ctx || table_bytes < sizeof(LtGatherRec) || iters < 1 || blocks_per_sm < 1 || blocks_per_sm > 16)
+  if (!ctx || ctx->group || table_bytes < sizeof(LtGatherRec) || iters < 1 || blocks_per_sm < 1 || blocks_per_sm > 16)
     return LT_ERR_INVALID;
   if (table_bytes / sizeof(LtGatherRec) > 0xffffffffull) return LT_ERR_INVALID;
   lt_stats st;

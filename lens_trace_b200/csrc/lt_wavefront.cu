@@ -50,7 +50,7 @@ __device__ __forceinline__ void pixel_of_path(long long path, int pixels, int wi
 // frame index, pixel and film position of a path: table look-up + exact multiply-shift division when the launch
 // has them (P.film), the reference's own operations otherwise
 struct LtWfPrimary;
-__device__ __forceinline__ void film_of_path(const LtWfPrimary& P, long long path, int pixels, int width, int height,
+__device__ __forceinline__ void film_of_path(const LtWfPrimary& P, long long path, int pixels, const LtLaunch& L,
                                              int& frameLocal, float& fx, float& fy);
 
 // queue entry v of [0, front + back): the front region grows from slot 0, the back region from the last slot
@@ -148,7 +148,7 @@ struct LtWfPrimary {
   int* aliveCount;
 };
 
-__device__ __forceinline__ void film_of_path(const LtWfPrimary& P, long long path, int pixels, int width, int height,
+__device__ __forceinline__ void film_of_path(const LtWfPrimary& P, long long path, int pixels, const LtLaunch& L,
                                              int& frameLocal, float& fx, float& fy) {
   if (P.film != nullptr) {
     frameLocal = (int)(((unsigned long long)path * P.divM) >> P.divS);
@@ -157,9 +157,9 @@ __device__ __forceinline__ void film_of_path(const LtWfPrimary& P, long long pat
     fy = f.y;
   } else {
     int px, py;
-    pixel_of_path(path, pixels, width, px, py, frameLocal);
-    fx = FADD(FDIV((float)px, (float)width), -0.5f);
-    fy = FADD(FDIV((float)py, (float)height), -0.5f);
+    pixel_of_path(path, pixels, L.width, px, py, frameLocal);
+    fx = FADD(FDIV((float)px, (float)L.width), -0.5f);
+    fy = FADD(FDIV((float)lt_image_row(L, py), (float)L.fullHeight), -0.5f);
   }
 }
 
@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_primary_trace(LtSceneDev sc, Lt
     int py = pixel / L.width, px = pixel - py * L.width;
     float fx, fy;
     Trav t;
-    t.r = camera_ray(L.cam, px, py, L.width, L.height, fx, fy);
+    t.r = camera_ray(L.cam, px, lt_image_row(L, py), L.width, L.fullHeight, fx, fy);
     LtCounters cnt = {0, 0, 0};
     trace<false>(t, sc, -1, lt_tinit(L.kernel), lt_eps(L.kernel), false, stk, list, cnt);
     P.hits[pixel] = make_float4(t.h.t, t.h.u, t.h.v,
@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_primary(LtSceneDev sc, LtLaunch
       int px = 0, py = 0, fl;
       float fx, fy;
       if (!STATS && primaryHits != nullptr) {
-        film_of_path(P, p, pixels, L.width, L.height, fl, fx, fy);  // the film position camera_ray computes
+        film_of_path(P, p, pixels, L, fl, fx, fy);  // the film position camera_ray computes
         float4 hv = primaryHits[(int)(p - (long long)fl * pixels)];
         unsigned hb = (unsigned)__float_as_int(hv.w);
         t.h.t = hv.x; t.h.u = hv.y; t.h.v = hv.z;
@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_primary(LtSceneDev sc, LtLaunch
         t.r.dz = 1.0f;
       } else {
         pixel_of_path(p, pixels, L.width, px, py, fl);
-        t.r = camera_ray(L.cam, px, py, L.width, L.height, fx, fy);
+        t.r = camera_ray(L.cam, px, lt_image_row(L, py), L.width, L.fullHeight, fx, fy);
         if (cull) trace_cull<STATS>(t, sc, -1, pc.tInit, pc.epsThr, stk, tstk, cnt);
         else trace<STATS>(t, sc, -1, pc.tInit, pc.epsThr, false, stk, list, cnt);
       }
@@ -431,7 +431,7 @@ __global__ void __launch_bounds__(WF_BLOCK, 8) k_wf_shade(LtSceneDev sc, LtLaunc
       ps.indirect[0] = dd.x; ps.indirect[1] = dd.y; ps.indirect[2] = dd.z;
       int fl;
       float fx, fy;
-      film_of_path(P, path, pixels, L.width, L.height, fl, fx, fy);
+      film_of_path(P, path, pixels, L, fl, fx, fy);
       unsigned sampleIndex = sample_index_of(L, pc, frame0 + fl, sample);
       bool done = shade_step(sc, pc, ps, r, h, fx, fy, sampleIndex, tStart, ignore, anyHit, lightHit ? 1 : 0);
       if (done) {

@@ -28,7 +28,8 @@ class RenderExtensionB200(C.Structure):
     _fields_ = [
         ("sType", C.c_int), ("pNext", C.c_void_p), ("frames", C.c_uint32), ("accumulate", C.c_uint32),
         ("maxRayDepth", C.c_uint32), ("collectStats", C.c_uint32), ("rays", C.c_uint64), ("nodeTests", C.c_uint64),
-        ("triTests", C.c_uint64), ("kernelMilliseconds", C.c_float),
+        ("triTests", C.c_uint64), ("kernelMilliseconds", C.c_float), ("deviceCount", C.c_uint32),
+        ("splitMode", C.c_uint32),
     ]
 
 
@@ -171,11 +172,12 @@ class Renderer:
             self.h = None
 
 
-def make_extension(frames=1, accumulate=False, max_ray_depth=0, collect_stats=False):
+def make_extension(frames=1, accumulate=False, max_ray_depth=0, collect_stats=False, devices=0, split=0):
     e = RenderExtensionB200()
     e.sType = STRUCTURE_TYPE_RENDER_EXTENSION_B200
     e.pNext = None
     e.frames, e.accumulate, e.maxRayDepth, e.collectStats = frames, int(accumulate), max_ray_depth, int(collect_stats)
+    e.deviceCount, e.splitMode = devices, split
     return e
 
 

@@ -47,7 +47,7 @@ void lt::retireObjectId(uint64_t id) {
   g_retireGeneration.fetch_add(1);
 }
 
-RendererB200::RendererB200() : ctx(nullptr), useCounter(0), seenRetireGeneration(0) {
+RendererB200::RendererB200() : ctx(nullptr), groupCtx(nullptr), groupDevices(0), useCounter(0), seenRetireGeneration(0) {
   if (lt_ctx_create(0, &ctx) != LT_OK) {
     printf("ERROR: %s\n", lt_last_error(nullptr));
     ctx = nullptr;
@@ -56,11 +56,18 @@ RendererB200::RendererB200() : ctx(nullptr), useCounter(0), seenRetireGeneration
 
 RendererB200::~RendererB200() {
   forgetScenes();
+  if (groupCtx) lt_ctx_destroy(groupCtx);
   if (ctx) lt_ctx_destroy(ctx);
 }
 
+static void releaseCached(lt_ctx* ctx, lt_ctx* groupCtx, lt_scene* scene, lt_scene* groupScene) {
+  if (scene) lt_scene_release(ctx, scene);
+  if (groupScene) lt_scene_release(groupCtx, groupScene);
+}
+
 void RendererB200::forgetScenes() {
-  for (size_t i = 0; i < sceneCache.size(); i++) lt_scene_release(ctx, sceneCache[i].scene);
+  for (size_t i = 0; i < sceneCache.size(); i++)
+    releaseCached(ctx, groupCtx, sceneCache[i].scene, sceneCache[i].groupScene);
   sceneCache.clear();
 }
 
@@ -117,7 +124,7 @@ void RendererB200::renderCommon(const std::string& kernelFilePath, KernelMode ke
     std::lock_guard<std::mutex> lock(g_retiredMutex);
     for (size_t i = 0; i < sceneCache.size();) {
       if (g_retired.count(sceneCache[i].asId) || g_retired.count(sceneCache[i].modelId)) {
-        lt_scene_release(ctx, sceneCache[i].scene);
+        releaseCached(ctx, groupCtx, sceneCache[i].scene, sceneCache[i].groupScene);
         sceneCache.erase(sceneCache.begin() + i);
       } else {
         i++;
@@ -130,39 +137,6 @@ void RendererB200::renderCommon(const std::string& kernelFilePath, KernelMode ke
   checksum = sample(checksum, as->getOrderedPrimitiveBuffer(), as->getOrderedPrimitiveBufferSize());
   checksum = sample(checksum, model->getMaterialBuffer(), model->getMaterialBufferSize());
   checksum = sample(checksum, as->getLightContainerBuffer(), as->getLightContainerBufferSize());
-  lt_scene* scene = nullptr;
-  for (size_t i = 0; i < sceneCache.size(); i++) {
-    CachedScene& c = sceneCache[i];
-    if (c.asId != as->getUniqueId() || c.modelId != model->getUniqueId()) continue;
-    if (c.checksum == checksum) {
-      scene = c.scene;
-      c.lastUse = ++useCounter;
-    } else {  // edited in place since the upload
-      lt_scene_release(ctx, c.scene);
-      sceneCache.erase(sceneCache.begin() + i);
-    }
-    break;
-  }
-  if (!scene) {
-    int rc = lt_scene_upload(ctx, as->getNodeBuffer(), as->getNodeBufferSize(), as->getOrderedPrimitiveBuffer(),
-                             as->getOrderedPrimitiveBufferSize(), model->getMaterialBuffer(),
-                             model->getMaterialBufferSize(), as->getLightContainerBuffer(),
-                             as->getLightContainerBufferSize(), &scene);
-    if (rc != LT_OK) {
-      printf("ERROR: scene upload failed: %s\n", lt_last_error(ctx));
-      return;
-    }
-    if (sceneCache.size() >= kMaxScenes) {  // bounded: the least recently used device copy goes
-      size_t oldest = 0;
-      for (size_t i = 1; i < sceneCache.size(); i++)
-        if (sceneCache[i].lastUse < sceneCache[oldest].lastUse) oldest = i;
-      lt_scene_release(ctx, sceneCache[oldest].scene);
-      sceneCache.erase(sceneCache.begin() + oldest);
-    }
-    CachedScene c = {as->getUniqueId(), model->getUniqueId(), checksum, ++useCounter, scene};
-    sceneCache.push_back(c);
-  }
-
   RenderExtensionB200* ext = nullptr;
   for (void* p = pNext; p;) {
     RenderExtensionB200* e = (RenderExtensionB200*)p;
@@ -172,6 +146,65 @@ void RendererB200::renderCommon(const std::string& kernelFilePath, KernelMode ke
     }
     p = e->pNext;
   }
+
+  // which context renders: the multi-GPU one when the extension asks for several devices (built-in pipelines only)
+  const uint32_t wantDevices = (ext && ext->deviceCount > 1 && plugin < 0) ? ext->deviceCount : 1;
+  if (wantDevices > 1 && (groupCtx == nullptr || groupDevices != wantDevices)) {
+    for (size_t i = 0; i < sceneCache.size(); i++)
+      if (sceneCache[i].groupScene) {
+        lt_scene_release(groupCtx, sceneCache[i].groupScene);
+        sceneCache[i].groupScene = nullptr;
+      }
+    if (groupCtx) lt_ctx_destroy(groupCtx);
+    groupCtx = nullptr;
+    std::vector<int> devices(wantDevices);
+    for (uint32_t d = 0; d < wantDevices; d++) devices[d] = (int)d;
+    if (lt_ctx_create_multi(devices.data(), (int)wantDevices, &groupCtx) != LT_OK) {
+      printf("ERROR: %s\n", lt_last_error(nullptr));
+      groupCtx = nullptr;
+      return;
+    }
+    groupDevices = wantDevices;
+  }
+  lt_ctx* useCtx = wantDevices > 1 ? groupCtx : ctx;
+  CachedScene* entry = nullptr;
+  for (size_t i = 0; i < sceneCache.size(); i++) {
+    CachedScene& c = sceneCache[i];
+    if (c.asId != as->getUniqueId() || c.modelId != model->getUniqueId()) continue;
+    if (c.checksum == checksum) {
+      entry = &c;
+      c.lastUse = ++useCounter;
+    } else {  // edited in place since the upload
+      releaseCached(ctx, groupCtx, c.scene, c.groupScene);
+      sceneCache.erase(sceneCache.begin() + i);
+    }
+    break;
+  }
+  if (!entry) {
+    if (sceneCache.size() >= kMaxScenes) {  // bounded: the least recently used device copy goes
+      size_t oldest = 0;
+      for (size_t i = 1; i < sceneCache.size(); i++)
+        if (sceneCache[i].lastUse < sceneCache[oldest].lastUse) oldest = i;
+      releaseCached(ctx, groupCtx, sceneCache[oldest].scene, sceneCache[oldest].groupScene);
+      sceneCache.erase(sceneCache.begin() + oldest);
+    }
+    CachedScene c = {as->getUniqueId(), model->getUniqueId(), checksum, ++useCounter, nullptr, nullptr};
+    sceneCache.push_back(c);
+    entry = &sceneCache.back();
+  }
+  lt_scene*& slot = wantDevices > 1 ? entry->groupScene : entry->scene;
+  if (!slot) {
+    int rc = lt_scene_upload(useCtx, as->getNodeBuffer(), as->getNodeBufferSize(), as->getOrderedPrimitiveBuffer(),
+                             as->getOrderedPrimitiveBufferSize(), model->getMaterialBuffer(),
+                             model->getMaterialBufferSize(), as->getLightContainerBuffer(),
+                             as->getLightContainerBufferSize(), &slot);
+    if (rc != LT_OK) {
+      printf("ERROR: scene upload failed: %s\n", lt_last_error(useCtx));
+      slot = nullptr;
+      return;
+    }
+  }
+  lt_scene* scene = slot;
 
   lt_render_params params;
   memset(&params, 0, sizeof params);
@@ -189,7 +222,8 @@ void RendererB200::renderCommon(const std::string& kernelFilePath, KernelMode ke
     params.frames = ext->frames ? (int)ext->frames : 1;
     params.accum_mode = ext->accumulate ? LT_ACCUM_RUNNING_MEAN : LT_ACCUM_NONE;
     params.max_ray_depth = (int)ext->maxRayDepth;
-    if (ext->collectStats) params.flags |= LT_FLAG_STATS;
+    if (ext->collectStats && wantDevices == 1) params.flags |= LT_FLAG_STATS;
+    params.split_mode = (int)ext->splitMode;
   }
   uint64_t need = sizeof(float) * imageDimensions[0] * imageDimensions[1] * imageDimensions[2];
   if (outputBufferSize < need) {
@@ -200,14 +234,14 @@ void RendererB200::renderCommon(const std::string& kernelFilePath, KernelMode ke
   int rc = plugin >= 0
                ? lt_render_plugin(ctx, scene, camera->getCameraBuffer(), plugin, params.kernel_mode, params.width,
                                   params.height, params.depth, params.block_x, params.block_y, (float*)pOutputBuffer)
-               : lt_render(ctx, scene, camera->getCameraBuffer(), &params, (float*)pOutputBuffer);
+               : lt_render(useCtx, scene, camera->getCameraBuffer(), &params, (float*)pOutputBuffer);
   if (rc != LT_OK) {
-    printf("Kernel Error: %d (%s)\n", rc, lt_last_error(ctx));
+    printf("Kernel Error: %d (%s)\n", rc, lt_last_error(useCtx));
     return;
   }
   if (ext) {
     lt_stats st;
-    lt_last_stats(ctx, &st);
+    lt_last_stats(useCtx, &st);
     ext->rays = st.rays;
     ext->nodeTests = st.node_tests;
     ext->triTests = st.tri_tests;

@@ -175,6 +175,11 @@ SceneParser::SceneParser(std::string filename) : parsedOk(false) {
     if (const JValue* v = r->get("frames")) rendererParsed.frames = (uint32_t)v->num;
     if (const JValue* v = r->get("accumulate")) rendererParsed.accumulate = v->kind == JValue::BOOL ? v->b : (v->num != 0);
     if (const JValue* v = r->get("max_ray_depth")) rendererParsed.maxRayDepth = (uint32_t)v->num;
+    if (const JValue* v = r->get("devices")) rendererParsed.deviceCount = (uint32_t)v->num;
+    if (const JValue* v = r->get("split")) {
+      if (isStr(v, "samples")) rendererParsed.splitMode = 1;
+      else if (isStr(v, "tiles")) rendererParsed.splitMode = 2;
+    }
   }
 
   if (const JValue* c = root.get("camera")) {
@@ -301,5 +306,7 @@ RenderExtensionB200 SceneParser::getRenderExtensionB200() {
   e.frames = rendererParsed.frames;
   e.accumulate = rendererParsed.accumulate;
   e.maxRayDepth = rendererParsed.maxRayDepth;
+  e.deviceCount = rendererParsed.deviceCount;
+  e.splitMode = rendererParsed.splitMode;
   return e;
 }

@@ -32,6 +32,10 @@ ACCUM_NONE = 0
 ACCUM_RUNNING_MEAN = 1
 ACCUM_WEIGHTED_SUM = 2
 
+SPLIT_AUTO = 0
+SPLIT_SAMPLES = 1
+SPLIT_TILES = 2
+
 FLAG_STATS = 1
 FLAG_CULL = 2
 FLAG_MEGAKERNEL = 4
