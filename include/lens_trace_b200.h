@@ -171,6 +171,13 @@ int lt_render(lt_ctx* ctx, lt_scene* scene, const void* camera28, const lt_rende
 int lt_render_device(lt_ctx* ctx, lt_scene* scene, const void* camera28, const lt_render_params* params,
                      float* device_out, int sync);
 
+/* The output buffer of the reference API is the caller's malloc'ed memory (pOutputBuffer, structures.h:62,76).
+ * lt_render copies into such pageable memory through its own pinned staging buffer; an application that reuses one
+ * buffer for many calls can page-lock it once instead, and the frame then arrives by a single DMA.  Unregister
+ * before freeing the buffer. */
+int lt_host_register(void* host_buffer, uint64_t bytes);
+int lt_host_unregister(void* host_buffer);
+
 /* The context-owned accumulator used by lt_render (reset = next running-mean frame restarts). */
 int lt_accum_reset(lt_ctx* ctx);
 int lt_accum_read(lt_ctx* ctx, float* host_out, uint64_t float_count);

@@ -114,10 +114,20 @@ struct LtSceneDev {
 
 // ------------------------------------------------------------------------------------------------
 // plug-in API (compiled only for plug-ins: NVRTC, or nvcc with -DLT_PLUGIN_API)
+//
+// The functions below are thin names over the library's OWN device code (lt_device.cuh, handed to NVRTC from memory
+// together with this header): lt_trace runs the same traversal the built-in pipelines run -- the stackless threaded
+// tree with one 256-bit load per box for small scenes, the child-pair tree with the traversal stack in shared memory
+// for large ones -- so a plug-in shader gets the tuned path and, where it follows the reference's kernels, the same
+// bits.  Shared memory: the library launches a plug-in that references `lt_scene` with the dynamic shared memory
+// lt_trace needs ((stack levels + 16) ints per thread); a plug-in must not declare dynamic shared memory of its own.
 // ------------------------------------------------------------------------------------------------
 #if defined(__CUDACC_RTC__) || defined(LT_PLUGIN_API)
 
 __constant__ LtSceneDev lt_scene;  // set by the library before each launch of a plug-in that references it
+
+#define LT_THREAD_STRIDE (blockDim.x * blockDim.y * blockDim.z)  // plug-ins run any block shape
+#include "lt_device.cuh"
 
 struct LtRay {
   float ox, oy, oz;  // origin
@@ -130,99 +140,91 @@ struct LtHit {
   int hitType;         // 1 = hit
 };
 
-__device__ __forceinline__ float lt_dot3z(float ax, float ay, float az, float bx, float by, float bz) {
-  return __fadd_rn(__fmaf_rn(az, bz, __fmaf_rn(ax, bx, __fmul_rn(ay, by))), 0.0f);
-}
+// |det| thresholds of intersectTriangle as the reference's kernel files compile them (the macro-defined epsilons
+// are compared in double precision): basic.cu / basic.cl / custom_opencl.cl / basic_lighting.cl, and the
+// accumulator / global-illumination files
+#define LT_EPSILON_BASIC 0x1.ad7f2ap-24f
+#define LT_EPSILON_GI 0x1.a36e30p-14f
 
-// intersectBounds (basic.cu:136-154) with dirIsNeg-selected bounds
-__device__ __forceinline__ bool lt_slab(float lox, float hix, float loy, float hiy, float loz, float hiz, const LtRay& r,
-                                        float ix, float iy, float iz) {
-  float tx0 = __fmul_rn(__fsub_rn(lox, r.ox), ix), tx1 = __fmul_rn(__fsub_rn(hix, r.ox), ix);
-  float ty0 = __fmul_rn(__fsub_rn(loy, r.oy), iy), ty1 = __fmul_rn(__fsub_rn(hiy, r.oy), iy);
-  float tz0 = __fmul_rn(__fsub_rn(loz, r.oz), iz), tz1 = __fmul_rn(__fsub_rn(hiz, r.oz), iz);
-  bool miss1 = (tx0 > ty1) || (ty0 > tx1);
-  float a = (ty0 > tx0) ? ty0 : tx0;
-  float b = (ty1 < tx1) ? ty1 : tx1;
-  bool miss2 = (a > tz1) || (tz0 > b);
-  float b2 = (tz1 < b) ? tz1 : b;
-  return !miss1 && !miss2 && (b2 > 0.0f);
-}
-
-// intersectTriangle (basic.cu:93-134); epsilon 1e-7f as in basic.cu
-__device__ __forceinline__ bool lt_triangle(int prim, const LtRay& r, float eps, LtHit& h) {
-  const float4* tp = reinterpret_cast<const float4*>(lt_scene.tris + prim);
-  float4 q0 = __ldg(tp), q1 = __ldg(tp + 1), q2 = __ldg(tp + 2);
-  float e1x = q0.w, e1y = q1.x, e1z = q1.y, e2x = q1.z, e2y = q1.w, e2z = q2.x;
-  float pvx = __fmaf_rn(r.dy, e2z, -__fmul_rn(r.dz, e2y));
-  float pvy = __fmaf_rn(r.dz, e2x, -__fmul_rn(r.dx, e2z));
-  float pvz = __fmaf_rn(r.dx, e2y, -__fmul_rn(r.dy, e2x));
-  float det = lt_dot3z(e1x, e1y, e1z, pvx, pvy, pvz);
-  if (fabsf(det) < eps) return false;
-  float inv = __frcp_rn(det);
-  float tx = __fsub_rn(r.ox, q0.x), ty = __fsub_rn(r.oy, q0.y), tz = __fsub_rn(r.oz, q0.z);
-  float u = __fmul_rn(lt_dot3z(tx, ty, tz, pvx, pvy, pvz), inv);
-  if (u < 0.0f || u > 1.0f) return false;
-  float qx = __fmaf_rn(ty, e1z, -__fmul_rn(tz, e1y));
-  float qy = __fmaf_rn(tz, e1x, -__fmul_rn(tx, e1z));
-  float qz = __fmaf_rn(tx, e1y, -__fmul_rn(ty, e1x));
-  float v = __fmul_rn(lt_dot3z(r.dx, r.dy, r.dz, qx, qy, qz), inv);
-  if (v < 0.0f || __fadd_rn(u, v) > 1.0f) return false;
-  float t = __fmul_rn(lt_dot3z(e2x, e2y, e2z, qx, qy, qz), inv);
-  if (t < h.t) {
-    h.t = t; h.u = u; h.v = v;
-    return true;
-  }
-  return false;
-}
-
-// The reference's intersect (ignorePrimitiveIndex < 0) / intersectIgnorePrimitiveIndex on the re-flattened scene.
-// tMax is the payload's initial t (the reference passes FLT_MAX = 1e7, basic.cu:1,308); anyHit stops at the first
-// accepted triangle (valid when only hitType is read, as the reference's shadow rays do).
-__device__ inline LtHit lt_trace(const LtRay& r, float tMax, int ignorePrimitiveIndex = -1, bool anyHit = false,
-                                 float epsilon = 1.00000001168609742e-07f) {
+// The reference's intersect (ignorePrimitiveIndex < 0) / intersectIgnorePrimitiveIndex (basic.cu:156-243): near
+// child first, strict t < best, no t > 0 test, first primitive of a leaf only.  tMax is the payload's initial t
+// (basic.cu passes its FLT_MAX = 1e7, the OpenCL files the real FLT_MAX).  anyHit stops at the first accepted
+// triangle (valid when only hitType is read, as the reference's shadow rays do).
+__device__ __forceinline__ LtHit lt_trace(const LtRay& r, float tMax, int ignorePrimitiveIndex = -1, bool anyHit = false,
+                                          float epsilon = LT_EPSILON_BASIC) {
+  extern __shared__ int lt_plugin_smem[];
+  const unsigned threads = blockDim.x * blockDim.y * blockDim.z;
+  const unsigned tid = (threadIdx.z * blockDim.y + threadIdx.y) * blockDim.x + threadIdx.x;
+  int* stk = lt_plugin_smem + tid;
+  int* list = lt_plugin_smem + (lt_scene.tnodes ? 0 : lt_stack_levels(lt_scene)) * threads + tid;
+  Trav t;
+  t.r.ox = r.ox; t.r.oy = r.oy; t.r.oz = r.oz;
+  t.r.dx = r.dx; t.r.dy = r.dy; t.r.dz = r.dz;
+  LtCounters cnt = {0, 0, 0};
+  trace<false>(t, lt_scene, ignorePrimitiveIndex, tMax, epsilon, anyHit, stk, list, cnt);
   LtHit h;
-  h.t = tMax; h.u = 0.0f; h.v = 0.0f; h.primitiveIndex = 0; h.hitType = 0;
-  float ix = __frcp_rn(r.dx), iy = __frcp_rn(r.dy), iz = __frcp_rn(r.dz);
-  bool nx = ix < 0.0f, ny = iy < 0.0f, nz = iz < 0.0f;
-  unsigned negMask = (nx ? 1u : 0u) | (ny ? 2u : 0u) | (nz ? 4u : 0u);
-  if (!lt_slab(nx ? lt_scene.rootMax[0] : lt_scene.rootMin[0], nx ? lt_scene.rootMin[0] : lt_scene.rootMax[0],
-               ny ? lt_scene.rootMax[1] : lt_scene.rootMin[1], ny ? lt_scene.rootMin[1] : lt_scene.rootMax[1],
-               nz ? lt_scene.rootMax[2] : lt_scene.rootMin[2], nz ? lt_scene.rootMin[2] : lt_scene.rootMax[2], r, ix, iy, iz))
-    return h;
-  int stack[64];
-  int sp = 0;
-  int cur = lt_scene.rootRef;
-  while (cur != LT_DONE) {
-    if (cur >= 0) {
-      const float4* np = reinterpret_cast<const float4*>(lt_scene.wnodes + cur);
-      float4 bx = __ldg(np), by = __ldg(np + 1), bz = __ldg(np + 2);
-      int4 m = __ldg(reinterpret_cast<const int4*>(np) + 3);
-      bool hl = lt_slab(nx ? bx.y : bx.x, nx ? bx.x : bx.y, ny ? by.y : by.x, ny ? by.x : by.y, nz ? bz.y : bz.x,
-                        nz ? bz.x : bz.y, r, ix, iy, iz);
-      bool hr = lt_slab(nx ? bx.w : bx.z, nx ? bx.z : bx.w, ny ? by.w : by.z, ny ? by.z : by.w, nz ? bz.w : bz.z,
-                        nz ? bz.z : bz.w, r, ix, iy, iz);
-      bool axisNeg = (negMask >> m.z) & 1u;
-      int nearRef = axisNeg ? m.y : m.x, farRef = axisNeg ? m.x : m.y;
-      bool hn = axisNeg ? hr : hl, hf = axisNeg ? hl : hr;
-      if (hn) {
-        cur = nearRef;
-        if (hf) stack[sp++] = farRef;
-      } else if (hf) {
-        cur = farRef;
-      } else {
-        cur = sp > 0 ? stack[--sp] : LT_DONE;
-      }
-    } else {
-      int prim = ~cur;
-      if (prim != ignorePrimitiveIndex && lt_triangle(prim, r, epsilon, h)) {
-        h.primitiveIndex = prim;
-        h.hitType = 1;
-        if (anyHit) return h;
-      }
-      cur = sp > 0 ? stack[--sp] : LT_DONE;
-    }
-  }
+  h.t = t.h.t; h.u = t.h.u; h.v = t.h.v;
+  h.primitiveIndex = t.h.prim;
+  h.hitType = t.h.hit;
   return h;
+}
+
+// shadow query (basic_lighting.cl:264-272): is anything but `ignorePrimitiveIndex` hit before tMax?
+__device__ __forceinline__ bool lt_occluded(const LtRay& r, float tMax, int ignorePrimitiveIndex = -1,
+                                            float epsilon = LT_EPSILON_BASIC) {
+  return lt_trace(r, tMax, ignorePrimitiveIndex, true, epsilon).hitType == 1;
+}
+
+// camera ray of pixel (px, py) (basic.cu:350-358); fx, fy receive the film position the hash RNG is keyed on
+__device__ __forceinline__ LtRay lt_camera_ray(const RefCamera& cam, int px, int py, int width, int height, float& fx,
+                                               float& fy) {
+  Ray c = camera_ray(cam, px, py, width, height, fx, fy);
+  LtRay r;
+  r.ox = c.ox; r.oy = c.oy; r.oz = c.oz;
+  r.dx = c.dx; r.dy = c.dy; r.dz = c.dz;
+  return r;
+}
+
+// random() of basic_lighting.cl:64-67 is lt_random(fx, fy, seed) (lt_device.cuh): fp64 fmod + sin, bit-exact.
+
+// uniformSampleHemisphere + alignHemisphereWithCoordinateSystem (global_illumination.cl:69-82); dir[3] = hemisphere.y,
+// the w the reference's float4 direction carries into its dot products
+__device__ __forceinline__ void lt_sample_hemisphere(float u1, float u2, const float up[3], float dir[4]) {
+  sample_hemisphere(u1, u2, up, dir);
+}
+
+// position and normal at barycentrics (u, v) of a primitive, unfused (basic_lighting.cl:236-244)
+__device__ __forceinline__ void lt_interpolate(int primitiveIndex, float u, float v, float position[3], float normal[3]) {
+  const RefPrim* p = lt_scene.prims + primitiveIndex;
+  const float w0 = bary0(u, v);
+  lerp_plain(p->a, p->b, p->c, w0, u, v, position);
+  lerp_plain(p->na, p->nb, p->nc, w0, u, v, normal);
+}
+
+__device__ __forceinline__ const RefMaterial& lt_material_of(int primitiveIndex) {
+  return lt_scene.mats[lt_scene.prims[primitiveIndex].materialIndex];
+}
+
+__device__ __forceinline__ bool lt_is_light(int primitiveIndex) { return is_light(lt_scene, primitiveIndex); }
+
+// light sample (basic_lighting.cl:246-262) from three random numbers: the shadow ray from `position` towards the
+// sampled point of the sampled light primitive; returns the ray's tMax (distance - 0.01)
+__device__ __forceinline__ float lt_sample_light(const float position[3], float rIndex, float rU, float rV, LtRay& shadow) {
+  Ray s;
+  const float tMax = make_shadow_ray(lt_scene, position, rIndex, rU, rV, s);
+  shadow.ox = s.ox; shadow.oy = s.oy; shadow.oz = s.oz;
+  shadow.dx = s.dx; shadow.dy = s.dy; shadow.dz = s.dz;
+  return tMax;
+}
+
+// progressive accumulator (accumulator.frag:10-19): pixel = frameCount > 0 ? (sample + pixel * frameCount) / (frameCount + 1) : sample
+__device__ __forceinline__ void lt_accumulate(float* pixel, const float sample[3], unsigned frameCount) {
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    float v = sample[k];
+    if (frameCount > 0) v = __fdiv_rn(__fadd_rn(v, __fmul_rn(pixel[k], (float)frameCount)), (float)(frameCount + 1u));
+    pixel[k] = v;
+  }
 }
 
 #endif  // plug-in API

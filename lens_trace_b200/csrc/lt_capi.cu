@@ -10,6 +10,7 @@
 #include <string.h>
 
 #include <string>
+#include <thread>
 #include <vector>
 
 static thread_local std::string g_error = "";
@@ -91,6 +92,8 @@ extern "C" void lt_ctx_destroy(lt_ctx* ctx) {
   if (ctx->dWork) cudaFree(ctx->dWork);
   if (ctx->wfWorkspace) cudaFree(ctx->wfWorkspace);
   if (ctx->dCamera) cudaFree(ctx->dCamera);
+  if (ctx->stage) cudaFreeHost(ctx->stage);
+  for (cudaEvent_t e : ctx->stageEvents) cudaEventDestroy(e);
   for (LtPlugin* p : ctx->plugins) lt_plugin_free(p);
   for (cudaEvent_t e : ctx->traceEvents) cudaEventDestroy(e);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -689,6 +692,83 @@ int lt_internal_render_rows(lt_ctx* ctx, lt_scene* scene, const void* camera28, 
   return render_common(ctx, scene, L, device_out, sync != 0);
 }
 
+// Result -> the caller's host buffer.  The reference hands render() a malloc'ed (pageable) pOutputBuffer
+// (src/cuda/renderer_cuda.cpp:137-139: cuMemcpyDtoH); a plain cudaMemcpy into pageable memory runs at a third of the
+// link rate because the driver stages it in small pieces.  Here: pinned or registered destinations get one DMA; a
+// pageable destination is filled through the context's own pinned staging buffer in 2 MB chunks -- the DMA of chunk
+// k+1 overlaps the host-side copy of chunk k, and the host side is spread over a few threads.  (Registering the
+// caller's buffer behind its back is not an option: a cached registration outlives a free()/mmap() of the same
+// address range and would then receive the frame in pages the caller no longer sees.)
+static int download(lt_ctx* ctx, float* host_out, const float* dSrc, size_t bytes) {
+  cudaPointerAttributes attr;
+  memset(&attr, 0, sizeof attr);
+  const bool pinned = cudaPointerGetAttributes(&attr, host_out) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+  cudaGetLastError();
+  static int threadsEnv = -1, minBytes = -1;
+  if (threadsEnv < 0) {
+    const char* e = getenv("LT_DOWNLOAD_THREADS");
+    threadsEnv = e ? atoi(e) : 4;
+    e = getenv("LT_DOWNLOAD_STAGED_MIN_BYTES");
+    minBytes = e ? atoi(e) : (1 << 20);
+  }
+  if (pinned || threadsEnv <= 0 || bytes < (size_t)minBytes) {
+    CK(cudaMemcpyAsync(host_out, dSrc, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return LT_OK;
+  }
+  const size_t kChunk = 2u << 20, kMaxStage = 256u << 20;
+  if (ctx->stageBytes < (bytes < kMaxStage ? bytes : kMaxStage)) {
+    if (ctx->stage) cudaFreeHost(ctx->stage);
+    ctx->stage = nullptr;
+    ctx->stageBytes = 0;
+    size_t want = bytes < kMaxStage ? bytes : kMaxStage;
+    want = (want + kChunk - 1) / kChunk * kChunk;
+    if (cudaMallocHost(&ctx->stage, want) != cudaSuccess) {  // no pinned memory to be had: the plain copy still works
+      cudaGetLastError();
+      CK(cudaMemcpyAsync(host_out, dSrc, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+      return LT_OK;
+    }
+    ctx->stageBytes = want;
+  }
+  for (size_t done = 0; done < bytes;) {  // one pass unless the frame exceeds the staging buffer
+    const size_t pass = bytes - done < ctx->stageBytes ? bytes - done : ctx->stageBytes;
+    const int chunks = (int)((pass + kChunk - 1) / kChunk);
+    while ((int)ctx->stageEvents.size() < chunks) {
+      cudaEvent_t e;
+      CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      ctx->stageEvents.push_back(e);
+    }
+    for (int c = 0; c < chunks; c++) {
+      const size_t off = (size_t)c * kChunk, n = pass - off < kChunk ? pass - off : kChunk;
+      CK(cudaMemcpyAsync(ctx->stage + off, (const char*)dSrc + done + off, n, cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaEventRecord(ctx->stageEvents[c], ctx->stream));
+    }
+    const int T = threadsEnv < chunks ? threadsEnv : chunks;
+    std::vector<cudaError_t> errs(T, cudaSuccess);
+    auto work = [&](int t) {
+      cudaSetDevice(ctx->device);
+      for (int c = t; c < chunks; c += T) {
+        cudaError_t e = cudaEventSynchronize(ctx->stageEvents[c]);
+        if (e != cudaSuccess) {
+          errs[t] = e;
+          return;
+        }
+        const size_t off = (size_t)c * kChunk, n = pass - off < kChunk ? pass - off : kChunk;
+        memcpy((char*)host_out + done + off, ctx->stage + off, n);
+      }
+    };
+    std::vector<std::thread> workers;
+    for (int t = 1; t < T; t++) workers.emplace_back(work, t);
+    work(0);
+    for (std::thread& w : workers) w.join();
+    for (int t = 0; t < T; t++)
+      if (errs[t] != cudaSuccess) return fail(ctx, LT_ERR_CUDA, std::string("download: ") + cudaGetErrorString(errs[t]));
+    done += pass;
+  }
+  return LT_OK;
+}
+
 extern "C" int lt_render(lt_ctx* ctx, lt_scene* scene, const void* camera28, const lt_render_params* params,
                          float* host_out) {
   if (ctx && ctx->group) return lt_multi_render(ctx, scene, camera28, params, host_out);
@@ -701,7 +781,7 @@ extern "C" int lt_render(lt_ctx* ctx, lt_scene* scene, const void* camera28, con
   if (rc != LT_OK) return rc;
   rc = render_common(ctx, scene, L, ctx->dOut, true);
   if (rc != LT_OK) return rc;
-  if (host_out) CK(cudaMemcpy(host_out, ctx->dOut, floats * sizeof(float), cudaMemcpyDeviceToHost));
+  if (host_out) return download(ctx, host_out, ctx->dOut, floats * sizeof(float));
   return LT_OK;
 }
 
@@ -741,7 +821,34 @@ extern "C" int lt_render_plugin(lt_ctx* ctx, lt_scene* scene, const void* camera
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaEventElapsedTime(&ctx->stats.kernel_ms, ctx->ev0, ctx->ev1));
   ctx->stats.kernel_launches = 1;
-  if (host_out) CK(cudaMemcpy(host_out, ctx->dOut, floats * sizeof(float), cudaMemcpyDeviceToHost));
+  if (host_out) return download(ctx, host_out, ctx->dOut, floats * sizeof(float));
+  return LT_OK;
+}
+
+// Opt-in for applications that keep one output buffer alive across many render() calls (the progressive examples):
+// a registered buffer receives the frame by a single DMA.  The caller owns the lifetime: unregister before free().
+extern "C" int lt_host_register(void* host_buffer, uint64_t bytes) {
+  if (!host_buffer || bytes == 0) return fail(nullptr, LT_ERR_INVALID, "lt_host_register: bad argument");
+  cudaError_t e = cudaHostRegister(host_buffer, bytes, cudaHostRegisterPortable);
+  if (e == cudaErrorHostMemoryAlreadyRegistered) {
+    cudaGetLastError();
+    return LT_OK;
+  }
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(nullptr, e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? LT_ERR_NO_DEVICE : LT_ERR_CUDA,
+                std::string("lt_host_register: ") + cudaGetErrorString(e));
+  }
+  return LT_OK;
+}
+
+extern "C" int lt_host_unregister(void* host_buffer) {
+  if (!host_buffer) return fail(nullptr, LT_ERR_INVALID, "lt_host_unregister: bad argument");
+  cudaError_t e = cudaHostUnregister(host_buffer);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(nullptr, LT_ERR_CUDA, std::string("lt_host_unregister: ") + cudaGetErrorString(e));
+  }
   return LT_OK;
 }
 

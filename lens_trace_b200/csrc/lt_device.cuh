@@ -2,12 +2,25 @@
 // wavefront pipeline (lt_wavefront.cu): exact-arithmetic helpers, the resumable traversal, camera ray,
 // frame combiner, hash RNG, light / hemisphere sampling and the per-ray shading step.
 #pragma once
-#include "lt_internal.h"
+#include "lt_device_types.h"
 
+#ifndef __CUDACC_RTC__
 #include <float.h>
 #include <math.h>
+#else  // NVRTC (plug-in kernels): no host headers
+#ifndef FLT_MAX
+#define FLT_MAX 3.402823466e+38F
+#endif
+#endif
 
 #define LT_BLOCK 128
+// Per-thread stacks and leaf FIFOs live in shared memory as [level][thread]: LT_THREAD_STRIDE ints between the levels
+// of one thread.  The library's kernels run blocks of LT_BLOCK threads; a plug-in build (any block shape) defines
+// the stride as its run-time block size before including this file.
+#ifndef LT_THREAD_STRIDE
+#define LT_THREAD_STRIDE LT_BLOCK
+#endif
+#define LT_LEVEL_BYTES ((unsigned)(LT_THREAD_STRIDE) * 4u)
 
 // ------------------------------------------------------------------------------------------------
 // exact-arithmetic helpers: never contracted, independent of -fmad
@@ -161,7 +174,7 @@ __device__ __forceinline__ int trav_pop(Trav& t, const int* __restrict__ stk) {
   // branch-free: an empty stack yields LT_DONE (slot 0 is read but not used)
   bool can = t.sp > 0;
   t.sp -= can ? 1 : 0;
-  int v = stk[t.sp * LT_BLOCK];
+  int v = stk[t.sp * LT_THREAD_STRIDE];
   return can ? v : LT_DONE;
 }
 
@@ -174,7 +187,6 @@ __device__ __forceinline__ int lds32(unsigned addr) {
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
   return v;
 }
-#define LT_SMEM_STRIDE_LOG2 9  // LT_BLOCK * sizeof(int) = 512 bytes between levels of one thread
 
 // One 256-bit read-only load (LDG.E.ENL2.256.CONSTANT, sm_100): a 32-byte record costs one L1 request -- and, for
 // the divergent addresses of a traversal, one wavefront per distinct 128-byte line -- instead of two.
@@ -221,7 +233,7 @@ __device__ __forceinline__ void trav_node_step(Trav& t, const LtSceneDev& sc, in
   bool both = hn && hf, none = !hn && !hf;
   bool canPop = none && t.sp > 0;
   t.sp -= canPop ? 1 : 0;
-  int slot = t.sp * LT_BLOCK;
+  int slot = t.sp * LT_THREAD_STRIDE;
   int popped = stk[slot];
   if (both) stk[slot] = farRef;
   t.sp += both ? 1 : 0;
@@ -247,7 +259,7 @@ __device__ __forceinline__ int trav_collect(Trav& t, const LtSceneDev& sc, int* 
     } else {
       int prim = ~t.cur;
       if (prim != t.ignore) {
-        list[n * LT_BLOCK] = prim;
+        list[n * LT_THREAD_STRIDE] = prim;
         n++;
       }
       t.cur = trav_pop(t, stk);
@@ -262,7 +274,7 @@ template <bool STATS>
 __device__ __forceinline__ bool trav_test(Trav& t, const LtSceneDev& sc, const int* __restrict__ list, int n,
                                           float epsThr, LtCounters& cnt) {
   for (int i = 0; i < n; i++) {
-    int prim = list[i * LT_BLOCK];
+    int prim = list[i * LT_THREAD_STRIDE];
     if (STATS) cnt.triTests++;
     if (tri_test(sc.tris, prim, t.r, epsThr, t.h)) {
       t.h.prim = prim;
@@ -297,7 +309,7 @@ __device__ __forceinline__ bool trav_iter(Trav& t, const LtSceneDev& sc, int* __
       if (leaf) {
         int prim = ~t.cur;
         if (prim != t.ignore) {
-          list[(t.qTail & (LT_MAX_BATCH - 1)) * LT_BLOCK] = prim;
+          list[(t.qTail & (LT_MAX_BATCH - 1)) * LT_THREAD_STRIDE] = prim;
           t.qTail++;
         }
         t.cur = trav_pop(t, stk);
@@ -306,7 +318,7 @@ __device__ __forceinline__ bool trav_iter(Trav& t, const LtSceneDev& sc, int* __
     if (t.cur == LT_DONE || t.qTail - t.qHead >= LT_MAX_BATCH) break;
   }
   for (int k = 0; k < triTests && t.qHead != t.qTail; k++) {
-    int prim = list[(t.qHead & (LT_MAX_BATCH - 1)) * LT_BLOCK];
+    int prim = list[(t.qHead & (LT_MAX_BATCH - 1)) * LT_THREAD_STRIDE];
     t.qHead++;
     if (STATS) cnt.triTests++;
     if (tri_test(sc.tris, prim, t.r, epsThr, t.h)) {
@@ -365,11 +377,11 @@ __device__ __forceinline__ bool trav_iter_lean(Trav& t, const LtSceneDev& sc, un
       bool farNow = hf && !nearInner;            // far is next in order right away
       bool recFar = farNow && farRef < 0 && ~farRef != t.ignore;
       if (recNear) {
-        sts32(fifoAddr + ((unsigned)(t.qTail & (LT_MAX_BATCH - 1)) << LT_SMEM_STRIDE_LOG2), ~nearRef);
+        sts32(fifoAddr + ((unsigned)(t.qTail & (LT_MAX_BATCH - 1)) * LT_LEVEL_BYTES), ~nearRef);
         t.qTail++;
       }
       if (recFar) {
-        sts32(fifoAddr + ((unsigned)(t.qTail & (LT_MAX_BATCH - 1)) << LT_SMEM_STRIDE_LOG2), ~farRef);
+        sts32(fifoAddr + ((unsigned)(t.qTail & (LT_MAX_BATCH - 1)) * LT_LEVEL_BYTES), ~farRef);
         t.qTail++;
       }
       bool push = hf && nearInner;
@@ -377,7 +389,7 @@ __device__ __forceinline__ bool trav_iter_lean(Trav& t, const LtSceneDev& sc, un
       bool pop = !nearInner && !farInner;
       bool canPop = pop && t.sp > 0;
       t.sp -= canPop ? 1 : 0;
-      unsigned slot = stkAddr + ((unsigned)t.sp << LT_SMEM_STRIDE_LOG2);
+      unsigned slot = stkAddr + ((unsigned)t.sp * LT_LEVEL_BYTES);
       int popped = lds32(slot);
       if (push) sts32(slot, farRef);
       t.sp += push ? 1 : 0;
@@ -387,17 +399,17 @@ __device__ __forceinline__ bool trav_iter_lean(Trav& t, const LtSceneDev& sc, un
     if (t.cur < 0 && t.cur != LT_DONE) {
       int prim = ~t.cur;
       if (prim != t.ignore) {
-        sts32(fifoAddr + ((unsigned)(t.qTail & (LT_MAX_BATCH - 1)) << LT_SMEM_STRIDE_LOG2), prim);
+        sts32(fifoAddr + ((unsigned)(t.qTail & (LT_MAX_BATCH - 1)) * LT_LEVEL_BYTES), prim);
         t.qTail++;
       }
       bool can = t.sp > 0;
       t.sp -= can ? 1 : 0;
-      int v = lds32(stkAddr + ((unsigned)t.sp << LT_SMEM_STRIDE_LOG2));
+      int v = lds32(stkAddr + ((unsigned)t.sp * LT_LEVEL_BYTES));
       t.cur = can ? v : LT_DONE;
     }
   }
   for (int k = 0; k < triTests && t.qHead != t.qTail; k++) {
-    int prim = lds32(fifoAddr + ((unsigned)(t.qHead & (LT_MAX_BATCH - 1)) << LT_SMEM_STRIDE_LOG2));
+    int prim = lds32(fifoAddr + ((unsigned)(t.qHead & (LT_MAX_BATCH - 1)) * LT_LEVEL_BYTES));
     t.qHead++;
     if (STATS) cnt.triTests++;
     if (tri_test(sc.tris, prim, t.r, epsThr, t.h)) {
@@ -465,7 +477,7 @@ __device__ __forceinline__ void trav_threaded_nodes(Trav& t, const LtThreadNode*
     }
     int link = __float_as_int(b.z), skip = __float_as_int(b.w);
     if (hit && link < 0 && link != notIgnore) {
-      sts32(fifoAddr + ((unsigned)(t.qTail & (LT_MAX_BATCH - 1)) << LT_SMEM_STRIDE_LOG2), ~link);
+      sts32(fifoAddr + ((unsigned)(t.qTail & (LT_MAX_BATCH - 1)) * LT_LEVEL_BYTES), ~link);
       t.qTail++;
     }
     t.cur = (hit && link >= 0) ? t.cur + 1 : skip;
@@ -482,7 +494,7 @@ __device__ __forceinline__ bool trav_iter_threaded(Trav& t, const LtThreadNode* 
   if (exact) trav_threaded_nodes<true>(t, tn, fifoAddr, maxSteps, notIgnore);
   else trav_threaded_nodes<false>(t, tn, fifoAddr, maxSteps, notIgnore);
   for (int k = 0; k < triTests && t.qHead != t.qTail; k++) {
-    int prim = lds32(fifoAddr + ((unsigned)(t.qHead & (LT_MAX_BATCH - 1)) << LT_SMEM_STRIDE_LOG2));
+    int prim = lds32(fifoAddr + ((unsigned)(t.qHead & (LT_MAX_BATCH - 1)) * LT_LEVEL_BYTES));
     t.qHead++;
     if (tri_test(tris, prim, t.r, epsThr, t.h)) {
       t.h.prim = prim;
@@ -552,8 +564,8 @@ __device__ __forceinline__ void trav_step_cull(Trav& t, const LtSceneDev& sc, in
     if (hn) {
       t.cur = nearRef;
       if (hf) {
-        stk[t.sp * LT_BLOCK] = farRef;
-        tstk[t.sp * LT_BLOCK] = farEntry;
+        stk[t.sp * LT_THREAD_STRIDE] = farRef;
+        tstk[t.sp * LT_THREAD_STRIDE] = farEntry;
         t.sp++;
       }
       return;
@@ -577,8 +589,8 @@ __device__ __forceinline__ void trav_step_cull(Trav& t, const LtSceneDev& sc, in
   t.cur = LT_DONE;
   while (t.sp > 0) {
     t.sp--;
-    if (!(tstk[t.sp * LT_BLOCK] > lim)) {
-      t.cur = stk[t.sp * LT_BLOCK];
+    if (!(tstk[t.sp * LT_THREAD_STRIDE] > lim)) {
+      t.cur = stk[t.sp * LT_THREAD_STRIDE];
       break;
     }
   }
@@ -594,9 +606,11 @@ __device__ __forceinline__ void trace_cull(Trav& t, const LtSceneDev& sc, int ig
 // dynamic shared memory of every traversal kernel: [stackDepth][LT_BLOCK] stack, [LT_MAX_BATCH][LT_BLOCK] leaf
 // list/FIFO, [stackDepth][LT_BLOCK] entry distances (culled mode only)
 __host__ __device__ inline int lt_stack_levels(const LtSceneDev& sc) { return sc.stackDepth < 1 ? 1 : sc.stackDepth; }
+#ifndef __CUDACC_RTC__
 __host__ inline size_t lt_traversal_smem(const LtSceneDev& sc, bool cull) {
   return (size_t)(lt_stack_levels(sc) * (cull ? 2 : 1) + LT_MAX_BATCH) * LT_BLOCK * sizeof(int);
 }
+#endif
 #define LT_SMEM_POINTERS(sc)                                                            \
   extern __shared__ int smemStack[];                                                    \
   int* stk = smemStack + threadIdx.x;                                                   \

@@ -6,31 +6,7 @@
 
 #include "lens_trace_b200_device.cuh"  // buffer layouts shared with plug-in kernels
 
-struct LtLaunch {
-  int kernel;        // lt_kernel
-  int kernelMode;    // 0 linear, 1 tile
-  int width, height, depth;
-  int maxRayDepth;
-  int frames;
-  unsigned frameStride;
-  int accumMode;
-  float accumWeight;
-  int flags;
-  int refillThreshold;  // k_path: leave the traversal loop when fewer lanes than this still have a ray
-  int batchAnyHit;      // k_path: leaves recorded before a shadow ray tests them (early-out granularity)
-  int batchClosest;     // k_path: leaves recorded before a closest-hit ray tests them
-  int iterNodeSteps;    // trav_iter: box-pair tests per iteration of a persistent loop
-  int iterTriTests;     // trav_iter: triangle tests per iteration
-  // Row window of a tile split (multi-GPU): this launch renders `height` rows of an image of `fullHeight` rows;
-  // local row j is image row ((j / rowBlock) * rowStride + rowPhase) * rowBlock + j % rowBlock (blocks of rowBlock
-  // rows dealt round-robin to rowStride devices).  rowStride <= 1: the whole image (fullHeight == height).
-  int fullHeight, rowBlock, rowStride, rowPhase;
-  RefCamera cam;
-};
-
-struct LtCounters {
-  unsigned long long rays, nodeTests, triTests;
-};
+#include "lt_device_types.h"  // LtLaunch, LtCounters (shared with plug-in builds)
 
 struct lt_ctx;
 int lt_internal_ctx_device(const lt_ctx* ctx);  // lt_capi.cu
@@ -106,6 +82,9 @@ struct lt_ctx {
   size_t wfBytes = 0;
   LtWfAux wfAux = {};           // second stream + events for overlapping consecutive wavefront batches
   size_t totalMem = 0;
+  char* stage = nullptr;  // pinned staging buffer of lt_render's copy into a pageable destination
+  size_t stageBytes = 0;
+  std::vector<cudaEvent_t> stageEvents;  // one per 2 MB chunk
   lt_stats stats = {};
 };
 

@@ -14,6 +14,7 @@
 //  * All FP32 arithmetic is written with explicit round-to-nearest intrinsics in the operation
 //    order the reference compiles to, so results do not depend on compiler contraction.
 //  * Tensor cores are not used: nothing here is a dense contraction.
+#include "lt_internal.h"
 #include "lt_device.cuh"
 
 #include <cub/device/device_scan.cuh>

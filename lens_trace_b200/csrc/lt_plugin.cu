@@ -37,6 +37,7 @@ struct Api {
                            void**, void**);
   CUresult (*moduleGetGlobal)(CUdeviceptr*, size_t*, CUmodule, const char*);
   CUresult (*memcpyHtoDAsync)(CUdeviceptr, const void*, size_t, CUstream);
+  CUresult (*funcSetAttribute)(CUfunction, CUfunction_attribute, int);
 };
 
 Api g_api;
@@ -68,7 +69,8 @@ bool load_api() {
          sym(rtc, "nvrtcDestroyProgram", a.destroyProgram, a.why) && sym(drv, "cuModuleLoadData", a.moduleLoadData, a.why) &&
          sym(drv, "cuModuleUnload", a.moduleUnload, a.why) && sym(drv, "cuModuleGetFunction", a.moduleGetFunction, a.why) &&
          sym(drv, "cuLaunchKernel", a.launchKernel, a.why) && sym(drv, "cuModuleGetGlobal_v2", a.moduleGetGlobal, a.why) &&
-         sym(drv, "cuMemcpyHtoDAsync_v2", a.memcpyHtoDAsync, a.why);
+         sym(drv, "cuMemcpyHtoDAsync_v2", a.memcpyHtoDAsync, a.why) &&
+         sym(drv, "cuFuncSetAttribute", a.funcSetAttribute, a.why);
   return a.ok;
 }
 
@@ -81,10 +83,8 @@ struct LtPlugin {
   CUdeviceptr sceneSymbol = 0;  // address of the plug-in's `lt_scene` constant, 0 if it does not use the device API
 };
 
-// text of include/lens_trace_b200_device.cuh, handed to NVRTC as the header "lens_trace_b200_device.cuh"
-static const char* kDeviceApiHeader =
+// texts of include/lens_trace_b200_device.cuh, lt_device.cuh and lt_device_types.h, handed to NVRTC as headers
 #include "lt_device_api_embed.inc"
-    ;
 
 // Compiles `path`; on failure returns nullptr and the compiler log / reason in `err`.
 LtPlugin* lt_plugin_compile(const char* path, std::string* err) {
@@ -103,14 +103,17 @@ LtPlugin* lt_plugin_compile(const char* path, std::string* err) {
   while ((n = fread(buf, 1, sizeof buf, f)) > 0) src.append(buf, n);
   fclose(f);
   nvrtcProgram prog;
-  const char* headerNames[] = {"lens_trace_b200_device.cuh"};
-  const char* headerTexts[] = {kDeviceApiHeader};
-  if (g_api.createProgram(&prog, src.c_str(), path, 1, headerTexts, headerNames) != NVRTC_SUCCESS) {
+  const char* headerNames[] = {"lens_trace_b200_device.cuh", "lt_device.cuh", "lt_device_types.h"};
+  const char* headerTexts[] = {kEmbedDeviceApi, kEmbedDeviceCode, kEmbedDeviceTypes};
+  if (g_api.createProgram(&prog, src.c_str(), path, 3, headerTexts, headerNames) != NVRTC_SUCCESS) {
     *err = "nvrtcCreateProgram failed";
     return nullptr;
   }
-  const char* opts[] = {"--gpu-architecture=sm_100a"};
-  nvrtcResult rc = g_api.compileProgram(prog, 1, opts);
+  // NVRTC's defaults otherwise, as in the reference (renderer_cuda.cpp:28: no options): a user's a * b + c contracts
+  // exactly as it would there.  The library's own device code is written with explicit rounding intrinsics and does
+  // not depend on the contraction mode.
+  const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17"};
+  nvrtcResult rc = g_api.compileProgram(prog, 2, opts);
   if (rc != NVRTC_SUCCESS) {
     size_t ls = 0;
     g_api.getProgramLogSize(prog, &ls);
@@ -178,10 +181,21 @@ int lt_plugin_launch(LtPlugin* p, int kernelMode, const LtSceneDev* sceneDev, co
     *err = "plug-in block size exceeds 1024 threads";
     return -1;
   }
+  // a plug-in that uses the device API traverses with per-thread stacks / leaf FIFOs in dynamic shared memory
+  unsigned smem = 0;
+  if (p->sceneSymbol && sceneDev) {
+    const int levels = sceneDev->tnodes ? 0 : (sceneDev->stackDepth < 1 ? 1 : sceneDev->stackDepth);
+    smem = (unsigned)(levels + 16) * (unsigned)(bx * by) * 4u;
+    if (smem > 200u * 1024u) {
+      *err = "plug-in block too large for the traversal stacks of this scene (use a smaller block)";
+      return -1;
+    }
+    if (smem > 48u * 1024u) g_api.funcSetAttribute(fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem);
+  }
   void* args[] = {(void*)&dNodes, (void*)&dPrims, (void*)&dMats, (void*)&dLights, (void*)&dCamera,
                   (void*)&dOut,   (void*)&width,  (void*)&height, (void*)&depth};
   CUresult rc = g_api.launchKernel(fn, (unsigned)((width + bx - 1) / bx), (unsigned)((height + by - 1) / by), 1,
-                                   (unsigned)bx, (unsigned)by, 1, 0, (CUstream)stream, args, nullptr);
+                                   (unsigned)bx, (unsigned)by, 1, smem, (CUstream)stream, args, nullptr);
   if (rc != CUDA_SUCCESS) {
     *err = "cuLaunchKernel failed for plug-in " + p->path + " (CUresult " + std::to_string((int)rc) + ")";
     return -1;

@@ -13,6 +13,7 @@
 // In a round all rays are of one kind (all primary, all shadow, all extension), shading code runs on
 // dense arrays, and the running mean is applied in frame order, so results are bit-identical to
 // k_path's.  Path state lives in HBM (64 B/path) between rounds.
+#include "lt_internal.h"
 #include "lt_device.cuh"
 
 #define WF_BLOCK LT_BLOCK

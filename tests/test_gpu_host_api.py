@@ -369,3 +369,55 @@ def test_scene_cache_follows_object_identity_and_content():
     r.render(K, w, h, accel, model, cam)
     assert r.cached_scenes() == 1
     r.close(); accel.close(); model.close(); cam.close()
+
+
+def test_gi_kernel_as_a_plugin_on_the_device_api():
+    """the example's GI kernel re-written as a .cu plug-in on lt_trace / lt_occluded / lt_random /
+    lt_sample_light / lt_sample_hemisphere equals the built-in LT_KERNEL_GI pipeline bit for bit (4 bounces, several
+    frameCounts, Cornell box and the lens scene, a mesh large enough for the stack traversal), and its kernel time stays
+    within 1.5x of the built-in single-frame launch."""
+    from lens_trace_b200 import capi
+    ctx = capi.Context(0)
+    pid = ctx.plugin_load(os.path.join(util.ROOT, "tests", "plugins", "gi_plugin.cu"))
+    for name in ("cornell_box", "cornell_box_lens"):
+        sb = util.scene(name)
+        sc = ctx.upload(sb)
+        for frame in (0, 1, 9):
+            cam = util.default_camera(0.02, frame)
+            for block in ((8, 8), (32, 1), (16, 4)):
+                got = ctx.render_plugin(sc, cam, pid, 320, 200, block=block)
+                want = ctx.render(sc, cam, capi.make_params(L.KERNEL_GI, 320, 200, max_ray_depth=4))
+                util.assert_bit_equal(got, want, "%s frame %d block %s: GI plug-in vs built-in" % (name, frame, block))
+        sc.release()
+    # timing at 1080p on the Cornell box, one frame per launch
+    sb = util.scene("cornell_box")
+    sc = ctx.upload(sb)
+    cam = util.default_camera(0.0, 3)
+    t_plugin, t_builtin = [], []
+    for _ in range(5):
+        ctx.render_plugin(sc, cam, pid, 1920, 1080, block=(8, 8))
+        t_plugin.append(ctx.stats().kernel_ms)
+        ctx.render(sc, cam, capi.make_params(L.KERNEL_GI, 1920, 1080, max_ray_depth=4), want_output=False)
+        t_builtin.append(ctx.stats().kernel_ms)
+    print("GI plug-in %.3f ms, built-in %.3f ms" % (min(t_plugin), min(t_builtin)))
+    assert min(t_plugin) <= 1.5 * min(t_builtin), (min(t_plugin), min(t_builtin))
+    sc.release()
+    ctx.close()
+
+
+def test_gi_plugin_on_a_large_mesh(tmp_path):
+    """... and on a tree too large for the threaded copies (stack traversal in the plug-in's dynamic shared memory)."""
+    from lens_trace_b200 import capi
+    p = str(tmp_path / "synth.obj")
+    host.write_synthetic_scene(p, 200, 0x5EED)  # 80 012 triangles, 160 023 nodes
+    sb = host.load_scene_buffers(p)
+    ctx = capi.Context(0)
+    sc = ctx.upload(sb)
+    pid = ctx.plugin_load(os.path.join(util.ROOT, "tests", "plugins", "gi_plugin.cu"))
+    cam = util.default_camera(0.0, 2)
+    for block in ((8, 8), (32, 2)):
+        got = ctx.render_plugin(sc, cam, pid, 400, 240, block=block)
+        want = ctx.render(sc, cam, capi.make_params(L.KERNEL_GI, 400, 240, max_ray_depth=4))
+        util.assert_bit_equal(got, want, "synthetic mesh, block %s: GI plug-in vs built-in" % (block,))
+    sc.release()
+    ctx.close()
