@@ -515,6 +515,14 @@ def main():
     if world > 1:
         dist.all_reduce(counts)
     rays, node_tests, tri_tests = [float(x) for x in counts.tolist()]
+    # ... and of what the exact pipelines really trace: an extension ray that hits a light is traced once, its
+    # remaining depths are accumulated without retracing (the reference retraces the identical ray per depth)
+    ctx.render_device(scene, cam, make_step_params(L.FLAG_STATS | L.FLAG_STATS_TRACED), acc.data_ptr(), sync=True)
+    stt = ctx.stats()
+    counts_t = torch.tensor([stt.rays, stt.node_tests, stt.tri_tests], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(counts_t)
+    rays_t, node_tests_t, tri_tests_t = [float(x) for x in counts_t.tolist()]
     # The camera ray of a pixel is the same in every frame (the reference has no sub-pixel jitter), so the wavefront
     # pipeline traces it once per pixel per step and starts all `frames` paths of the pixel from that hit record.
     # rays / node_tests / tri_tests above are the reference's counts (one primary ray per pixel per frame); the
@@ -631,9 +639,9 @@ def main():
         # roofline of ONE GPU's kernels: the counters were summed over ranks
         shared_primary = launches_per_step > 1 and frames > 1  # the wavefront pipeline (exact mode) does this
         skipped = (frames - 1) * world if shared_primary else 0
-        rays_traced = rays - skipped * primary_counts[0]
-        node_traced = node_tests - skipped * primary_counts[1]
-        tri_traced = tri_tests - skipped * primary_counts[2]
+        rays_traced = rays_t - skipped * primary_counts[0]
+        node_traced = node_tests_t - skipped * primary_counts[1]
+        tri_traced = tri_tests_t - skipped * primary_counts[2]
         if kernel <= 2 and frames > 1:
             # deterministic kernels: every frame is the same image, k_flat traces once and applies the frame
             # combiner `frames` times in registers
@@ -723,6 +731,7 @@ def main():
                      "algorithmic_bytes_per_step": alg_bytes, "algorithmic_fp32_instr_per_step": alg_instr,
                      "traversal_set_bytes": traversal_bytes,
                      "rays_traced_per_step": rays_traced / world,
+                     "light_hit_retraces_folded_per_step": (rays - rays_t) / world,
                      "reference_rays_per_step": rays / world,
                      "reference_algorithmic_bytes_per_step": ref_alg_bytes,
                      "primary_rays": "traced once per pixel per step and shared by the step's %d frames "

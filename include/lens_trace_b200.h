@@ -68,6 +68,9 @@ enum lt_flags {
                                   both produce bit-identical output) */
   LT_FLAG_SERIAL = 1 << 5,     /* wavefront pipeline: one stream, one kernel at a time (default: consecutive batches
                                   overlap on two streams; identical output).  For timing kernels in isolation. */
+  LT_FLAG_STATS_TRACED = 1 << 7, /* with LT_FLAG_STATS: count what the exact pipelines really trace -- an extension ray
+                                    that hits a light is traced once, not once per remaining depth as the reference
+                                    does (global_illumination.cl:314-331; the picture is the same) */
   LT_FLAG_NO_STREAM = 1 << 6,  /* deterministic kernels on large scenes: one thread per pixel (k_flat) instead of the
                                   persistent warps that fetch pixel tiles (identical output; kept for comparison) */
   LT_FLAG_NO_THREADED = 1 << 4 /* small scenes: traverse with the stack kernels instead of the stackless threaded

@@ -9,11 +9,80 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
 
 static thread_local std::string g_error = "";
+
+// Copier threads of download(): they sleep between jobs; a job is `chunks` pieces of a pinned staging buffer to be
+// copied to the destination as soon as the owner has published them.
+struct LtCopyPool {
+  std::vector<std::thread> threads;
+  std::mutex m;
+  std::condition_variable wake;
+  bool quit = false;
+  unsigned long long job = 0;  // incremented per job (guards against spurious wake-ups)
+  char* dst = nullptr;
+  const char* src = nullptr;
+  size_t bytes = 0, chunk = 0;
+  int chunks = 0;
+  std::atomic<int> ready{0}, next{0}, copied{0};
+
+  explicit LtCopyPool(int n) {
+    for (int i = 0; i < n; i++) threads.emplace_back([this]() { run(); });
+  }
+  ~LtCopyPool() {
+    {
+      std::lock_guard<std::mutex> lock(m);
+      quit = true;
+    }
+    wake.notify_all();
+    for (std::thread& t : threads) t.join();
+  }
+  void copy_some() {
+    while (true) {
+      const int c = next.fetch_add(1);
+      if (c >= chunks) return;
+      while (ready.load(std::memory_order_acquire) <= c) std::this_thread::yield();
+      const size_t off = (size_t)c * chunk, n = bytes - off < chunk ? bytes - off : chunk;
+      memcpy(dst + off, src + off, n);
+      copied.fetch_add(1, std::memory_order_release);
+    }
+  }
+  void run() {
+    unsigned long long seen = 0;
+    while (true) {
+      {
+        std::unique_lock<std::mutex> lock(m);
+        wake.wait(lock, [&]() { return quit || job != seen; });
+        if (quit) return;
+        seen = job;
+      }
+      copy_some();
+    }
+  }
+  void begin(char* d, const char* s, size_t b, size_t c, int n) {
+    {
+      std::lock_guard<std::mutex> lock(m);
+      dst = d; src = s; bytes = b; chunk = c; chunks = n;
+      ready.store(0);
+      next.store(0);
+      copied.store(0);
+      job++;
+    }
+    wake.notify_all();
+  }
+  void publish(int n) { ready.store(n, std::memory_order_release); }
+  void finish() {  // the owner copies along, then waits for the stragglers
+    copy_some();
+    while (copied.load(std::memory_order_acquire) < chunks) std::this_thread::yield();
+  }
+};
+
 
 static int fail(lt_ctx* ctx, int code, const std::string& msg) {
   if (ctx) ctx->error = msg;
@@ -92,6 +161,7 @@ extern "C" void lt_ctx_destroy(lt_ctx* ctx) {
   if (ctx->dWork) cudaFree(ctx->dWork);
   if (ctx->wfWorkspace) cudaFree(ctx->wfWorkspace);
   if (ctx->dCamera) cudaFree(ctx->dCamera);
+  delete ctx->copyPool;
   if (ctx->stage) cudaFreeHost(ctx->stage);
   for (cudaEvent_t e : ctx->stageEvents) cudaEventDestroy(e);
   for (LtPlugin* p : ctx->plugins) lt_plugin_free(p);
@@ -717,6 +787,7 @@ static int download(lt_ctx* ctx, float* host_out, const float* dSrc, size_t byte
     return LT_OK;
   }
   const size_t kChunk = 2u << 20, kMaxStage = 256u << 20;
+  if (!ctx->copyPool) ctx->copyPool = new LtCopyPool(threadsEnv - 1);
   if (ctx->stageBytes < (bytes < kMaxStage ? bytes : kMaxStage)) {
     if (ctx->stage) cudaFreeHost(ctx->stage);
     ctx->stage = nullptr;
@@ -744,26 +815,18 @@ static int download(lt_ctx* ctx, float* host_out, const float* dSrc, size_t byte
       CK(cudaMemcpyAsync(ctx->stage + off, (const char*)dSrc + done + off, n, cudaMemcpyDeviceToHost, ctx->stream));
       CK(cudaEventRecord(ctx->stageEvents[c], ctx->stream));
     }
-    const int T = threadsEnv < chunks ? threadsEnv : chunks;
-    std::vector<cudaError_t> errs(T, cudaSuccess);
-    auto work = [&](int t) {
-      cudaSetDevice(ctx->device);
-      for (int c = t; c < chunks; c += T) {
-        cudaError_t e = cudaEventSynchronize(ctx->stageEvents[c]);
-        if (e != cudaSuccess) {
-          errs[t] = e;
-          return;
-        }
-        const size_t off = (size_t)c * kChunk, n = pass - off < kChunk ? pass - off : kChunk;
-        memcpy((char*)host_out + done + off, ctx->stage + off, n);
-      }
-    };
-    std::vector<std::thread> workers;
-    for (int t = 1; t < T; t++) workers.emplace_back(work, t);
-    work(0);
-    for (std::thread& w : workers) w.join();
-    for (int t = 0; t < T; t++)
-      if (errs[t] != cudaSuccess) return fail(ctx, LT_ERR_CUDA, std::string("download: ") + cudaGetErrorString(errs[t]));
+    // host side: a small pool of copier threads (no CUDA calls in them); this thread waits for the chunks' DMA and
+    // publishes how many have landed, then copies along
+    LtCopyPool& pool = *ctx->copyPool;
+    pool.begin((char*)host_out + done, ctx->stage, pass, kChunk, chunks);
+    cudaError_t err = cudaSuccess;
+    for (int c = 0; c < chunks; c++) {
+      cudaError_t e = cudaEventSynchronize(ctx->stageEvents[c]);
+      if (e != cudaSuccess && err == cudaSuccess) err = e;
+      pool.publish(c + 1);
+    }
+    pool.finish();
+    if (err != cudaSuccess) return fail(ctx, LT_ERR_CUDA, std::string("download: ") + cudaGetErrorString(err));
     done += pass;
   }
   return LT_OK;

@@ -926,6 +926,7 @@ struct PathConsts {
   bool whiteOnLight;  // accumulator.cl:233-238
   int samplesPerFrame;
   int maxDepth;
+  bool foldLightHits;  // see shade_step: a light hit's remaining depths are accumulated without retracing the ray
 };
 
 __device__ __forceinline__ PathConsts path_consts(const LtLaunch& L) {
@@ -936,6 +937,9 @@ __device__ __forceinline__ PathConsts path_consts(const LtLaunch& L) {
   pc.whiteOnLight = (L.kernel == 4);
   pc.samplesPerFrame = (L.kernel == 3 || L.kernel == 5) ? 25 : 1;
   pc.maxDepth = L.maxRayDepth > 0 ? L.maxRayDepth : 16;
+  // counting launches (LT_FLAG_STATS = 1) trace what the reference traces, unless LT_FLAG_STATS_TRACED = 128 asks for
+  // the counts of what the exact pipelines really trace
+  pc.foldLightHits = !(L.flags & 1) || (L.flags & 128);
   return pc;
 }
 
@@ -975,16 +979,21 @@ __device__ __forceinline__ bool shade_step(const LtSceneDev& sc, const PathConst
         ps.direct[0] = ps.direct[1] = ps.direct[2] = 1.0f;
         sampleDone = true;
       } else {
-        // dot(previousNormal (w = 1), direction (w = hemisphere.y)), global_illumination.cl:321;
-        // the ray is not advanced, so the same hit is found again at the next depth
-        float w = (float)__ddiv_rn(1.0, (double)(ps.depth + 1));
-        float d = FADD(FADD(FADD(FMUL(ps.nrm[0], r.dx), FMUL(ps.nrm[1], r.dy)), FMUL(ps.nrm[2], r.dz)),
-                       FMUL(1.0f, ps.extW));
-        float c = FMUL(FMUL(w, 1.0f), d);
-        ps.indirect[0] = FADD(ps.indirect[0], c);
-        ps.indirect[1] = FADD(ps.indirect[1], c);
-        ps.indirect[2] = FADD(ps.indirect[2], c);
-        ps.depth++;
+        // dot(previousNormal (w = 1), direction (w = hemisphere.y)), global_illumination.cl:321.
+        // The reference does not advance the ray, so it traces the same ray again at the next depth, finds the same
+        // hit (the hit is a function of the ray alone) and lands here again, until maxDepth.  Those traversals change
+        // nothing but the depth: the remaining terms 1/(depth+1) * d are added here, in the same order, without
+        // tracing (the counting launches still retrace, so that their counts are the reference's).
+        const float d = FADD(FADD(FADD(FMUL(ps.nrm[0], r.dx), FMUL(ps.nrm[1], r.dy)), FMUL(ps.nrm[2], r.dz)),
+                             FMUL(1.0f, ps.extW));
+        do {
+          float w = (float)__ddiv_rn(1.0, (double)(ps.depth + 1));
+          float c = FMUL(FMUL(w, 1.0f), d);
+          ps.indirect[0] = FADD(ps.indirect[0], c);
+          ps.indirect[1] = FADD(ps.indirect[1], c);
+          ps.indirect[2] = FADD(ps.indirect[2], c);
+          ps.depth++;
+        } while (pc.foldLightHits && ps.depth < pc.maxDepth);
         if (ps.depth >= pc.maxDepth) sampleDone = true;
         else retrace = true;
       }

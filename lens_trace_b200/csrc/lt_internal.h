@@ -61,7 +61,8 @@ int lt_plugin_launch(LtPlugin* p, int kernelMode, const LtSceneDev* sceneDev, co
 // ---- context and scene objects behind the C-ABI handles (lt_capi.cu; lt_multi.cu for multi-GPU contexts) ----
 #include <vector>
 #include "lens_trace_b200.h"
-struct LtGroup;  // lt_multi.cu: the devices of a multi-GPU context
+struct LtGroup;     // lt_multi.cu: the devices of a multi-GPU context
+struct LtCopyPool;  // lt_capi.cu: host threads that copy staged chunks into a pageable destination
 
 struct lt_ctx {
   int device = 0;
@@ -85,6 +86,7 @@ struct lt_ctx {
   char* stage = nullptr;  // pinned staging buffer of lt_render's copy into a pageable destination
   size_t stageBytes = 0;
   std::vector<cudaEvent_t> stageEvents;  // one per 2 MB chunk
+  LtCopyPool* copyPool = nullptr;
   lt_stats stats = {};
 };
 

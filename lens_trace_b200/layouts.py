@@ -41,6 +41,7 @@ FLAG_CULL = 2
 FLAG_MEGAKERNEL = 4
 FLAG_WAVEFRONT = 8
 FLAG_SERIAL = 32  # wavefront: no overlap of consecutive batches (timing kernels in isolation; same output)
+FLAG_STATS_TRACED = 128  # with FLAG_STATS: count the rays actually traced (light-hit retraces folded)
 FLAG_NO_STREAM = 64  # large scenes, deterministic kernels: one thread per pixel instead of tile-fetching persistent warps (same output)
 FLAG_NO_THREADED = 16  # small scenes: stack kernels instead of the stackless threaded tree (same output)
 

@@ -311,7 +311,7 @@ def test_registry_goes_by_content_through_the_renderer(tmp_path):
     # same NAME, edited colour store: must run as a plug-in and show the edit
     (tmp_path / "b").mkdir()
     edited = tmp_path / "b" / "basic.cu"
-    assert text.count("output[id + 0] = outputColor.x;") == 1
+    assert text.count("output[id + 0] = outputColor.x;") >= 1  # linearKernel and tileKernel
     edited.write_text(text.replace("output[id + 0] = outputColor.x;", "output[id + 0] = outputColor.x * 0.5f + 0.25f;"))
     assert capi.kernel_from_path(str(edited)) < 0
     got = r.render(str(edited), w, h, accel, model, cam, block=(8, 8))
