@@ -49,20 +49,21 @@ WORKLOADS = {
 DEFAULT_WORKLOAD = "cornell_gi_1080p_64spp"
 
 
-def load_scene(model):
+def load_scene(model, kind=0):
+    """kind: AccelerationStructureExplicitType (0 = the reference's median split, 101 = binned SAH, opt-in)"""
     from lens_trace_b200 import host
     if model.startswith("synth:"):
         n = int(model.split(":")[1])
         path = "/tmp/lt_synth_%d_%d.obj" % (n, os.getpid())
         host.write_synthetic_scene(path, n, 0x5EED)
-        sb = host.load_scene_buffers(path)
+        sb = host.load_scene_buffers(path, kind)
         for p in (path, path[:-4] + ".mtl"):
             try:
                 os.remove(p)
             except OSError:
                 pass
         return sb
-    return host.load_scene_buffers(os.path.join(ROOT, "resources", "models", model + ".obj"))
+    return host.load_scene_buffers(os.path.join(ROOT, "resources", "models", model + ".obj"), kind)
 
 
 def peaks():
@@ -856,6 +857,36 @@ def main():
                 "node_tests_per_ray": sl.node_tests / max(1, sl.rays), "tri_tests_per_ray": sl.tri_tests / max(1, sl.rays),
                 "pixels_differing_beyond_1e-4_rel": differing, "pixels": w * h}
             lscene.release()
+        if world == 1 and not args.no_lbvh:
+            # OPT-IN host builder with binned SAH splits (ACCELERATION_STRUCTURE_TYPE_SAH_B200): again a different tree
+            # in the same layout, same kernels, reported beside the headline only
+            ctx.set_stream(stream.cuda_stream)
+            t0 = time.perf_counter()
+            sb_sah = load_scene(model, 101)
+            sah_build_s = time.perf_counter() - t0
+            sscene = ctx.upload(sb_sah)
+            times = []
+            for _ in range(max(2, min(args.steps, 3)) + 1):
+                flush.fill_(1.0)
+                c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                c0.record(stream)
+                ctx.render_device(sscene, cam, make_step_params(), acc.data_ptr(), sync=False)
+                c1.record(stream)
+                torch.cuda.synchronize()
+                times.append(c0.elapsed_time(c1))
+            sms = sum(times[1:]) / len(times[1:])
+            differing = int(((acc - result_image).abs().amax(dim=-1) >
+                             1e-4 * result_image.abs().amax(dim=-1).clamp_min(1e-3)).sum().item())
+            ctx.render_device(sscene, cam, make_step_params(L.FLAG_STATS), acc.data_ptr(), sync=True)
+            ss = ctx.stats()
+            line["sah_opt_in"] = {
+                "what": "same workload on a binned-SAH tree built on the host (ACCELERATION_STRUCTURE_TYPE_SAH_B200), "
+                        "not the reference builder's tree",
+                "load_and_build_s_host": sah_build_s, "ms_per_step": sms, "value": ss.rays / (sms * 1e-3) / 1e6,
+                "unit": "Mrays/s", "speedup_vs_reference_tree": ms_per_step / sms,
+                "node_tests_per_ray": ss.node_tests / max(1, ss.rays), "tri_tests_per_ray": ss.tri_tests / max(1, ss.rays),
+                "pixels_differing_beyond_1e-4_rel": differing, "pixels": w * h}
+            sscene.release()
         if world == 1 and not args.no_ref_cuda:
             # the reference's CUDA kernel only exists for primary rays (basic.cu): the workload's scene, and -- because
             # a 42-triangle box says little about traversal -- the synthetic 1 M-triangle mesh (BASELINE configs[2])

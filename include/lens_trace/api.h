@@ -56,7 +56,9 @@ enum ImageType {
 enum AccelerationStructureExplicitType {
   ACCELERATION_STRUCTURE_TYPE_BVH,
   // --- B200 extension (not in the reference): LBVH built on the GPU (lt_scene_build_lbvh), same flattened layout
-  ACCELERATION_STRUCTURE_TYPE_LBVH_B200 = 100
+  ACCELERATION_STRUCTURE_TYPE_LBVH_B200 = 100,
+  // --- B200 extension: host builder with binned surface-area-heuristic splits, same flattened layout
+  ACCELERATION_STRUCTURE_TYPE_SAH_B200 = 101
 };
 
 struct ThreadOrganizationOpenCL {

@@ -105,6 +105,7 @@ class Model:
 class AccelerationStructure:
     HOST_MEDIAN_SPLIT = 0
     GPU_LBVH = 100
+    HOST_SAH = 101
 
     def __init__(self, model, kind=0):
         self.lib = load()
@@ -188,13 +189,14 @@ def write_synthetic_scene(path, grid_n, seed=0x5EED):
     return n
 
 
-def load_scene_buffers(obj_path):
-    """OBJ -> Model -> AccelerationStructureExplicit -> flat buffers (layouts.SceneBuffers)."""
+def load_scene_buffers(obj_path, kind=0):
+    """OBJ -> Model -> AccelerationStructureExplicit (kind: 0 median split, 100 GPU LBVH, 101 host SAH) -> flat
+    buffers (layouts.SceneBuffers)."""
     m = Model(obj_path)
     if m.primitive_count == 0:
         m.close()
         raise RuntimeError("model %s has no primitives" % obj_path)
-    a = AccelerationStructure(m)
+    a = AccelerationStructure(m, kind)
     sb = a.buffers()
     a.close()
     m.close()

@@ -7,6 +7,7 @@ import os
 import numpy as np
 import pytest
 
+import lt_oracle as O
 import util
 from lens_trace_b200 import capi, host, layouts as L
 
@@ -360,3 +361,22 @@ def test_unreachable_node_entries_are_rejected_on_the_host():
     with pytest.raises(capi.LtError) as e:
         capi.build_threaded(padded)
     assert "reachable" in str(e.value)
+
+
+@pytest.mark.parametrize("name", ["cornell_box", "cornell_box_lens", "green_wall"])
+def test_sah_builder_option(name):
+    """ACCELERATION_STRUCTURE_TYPE_SAH_B200: a valid tree in the reference layout over the same primitives, fewer box
+    tests per ray than the median split, the same picture except where a ray grazes an edge shared by two triangles."""
+    path = os.path.join(util.MODELS, name + ".obj")
+    sah = host.load_scene_buffers(path, host.AccelerationStructure.HOST_SAH)
+    med = util.scene(name)
+    _check_tree(sah)
+    assert len(sah.nodes) == len(med.nodes)
+    assert sorted(p.tobytes() for p in sah.prims) == sorted(p.tobytes() for p in med.prims)
+    assert sah.lights["count"][0] == med.lights["count"][0]
+    cam = util.default_camera(0.02)
+    a, sa = O.render(L.KERNEL_BASIC_CL, sah, cam, 200, 150, with_stats=True, threads=0)
+    b, sb = O.render(L.KERNEL_BASIC_CL, med, cam, 200, 150, with_stats=True, threads=0)
+    assert sa.nodeTests <= sb.nodeTests
+    assert (np.abs(a - b).max(axis=-1) > 0).mean() < 0.002
+    capi.build_threaded(sah.nodes)  # passes the upload-time validation
