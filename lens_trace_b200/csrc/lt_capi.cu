@@ -238,6 +238,7 @@ extern "C" void lt_scene_release(lt_ctx* ctx, lt_scene* s) {
   cudaFree(s->dWide);
   cudaFree(s->dTris);
   cudaFree(s->dThread);
+  cudaFree(s->dThreadBig);
   delete s;
 }
 
@@ -342,6 +343,25 @@ static int finish_scene(lt_ctx* ctx, lt_scene* s, int nNodes, int nPrims, int nM
       A(cudaStreamSynchronize(st));  // hThread is pageable and goes out of scope
     }
   }
+  // large trees: the threaded copies are built on the device and used by coherent-ray launches only (lt_kernels.cu:
+  // scene_for_flags); skipped when they would not fit the budget (LT_THREADED_COHERENT_MAX_BYTES, default 4 GB)
+  if (e == cudaSuccess && nNodes > lt_threaded_max_nodes() && nNodes > 1) {
+    static long long budget = -1;
+    if (budget < 0) {
+      const char* env = getenv("LT_THREADED_COHERENT_MAX_BYTES");
+      budget = env ? atoll(env) : (4ll << 30);
+    }
+    const size_t bytes = sizeof(LtThreadNode) * 8 * (size_t)nNodes;
+    if ((long long)bytes <= budget && bytes <= ctx->totalMem / 8 && (long long)nNodes * 8 < 0x7fffffffll) {
+      if (cudaMalloc(&s->dThreadBig, bytes) == cudaSuccess) {
+        lt_launch_build_threaded(s->dNodes, nNodes, s->dThreadBig, st);
+        A(cudaGetLastError());
+      } else {
+        cudaGetLastError();  // no memory for the copies: the stack traversal serves every launch
+        s->dThreadBig = nullptr;
+      }
+    }
+  }
   A(cudaEventRecord(ctx->ev1, st));
   A(cudaStreamSynchronize(st));
   cudaFree(dFlags);
@@ -369,6 +389,7 @@ static int finish_scene(lt_ctx* ctx, lt_scene* s, int nNodes, int nPrims, int nM
   d.primCount = nPrims;
   d.matCount = nMats;
   d.tnodes = s->dThread;
+  d.tnodesCoherent = s->dThreadBig;
   return LT_OK;
 }
 

@@ -15,6 +15,7 @@ int lt_internal_ctx_device(const lt_ctx* ctx);  // lt_capi.cu
 int lt_launch_reflatten(const RefNode* dNodes, int nodeCount, const RefPrim* dPrims, int primCount,
                         const int* dInnerRank, LtWideNode* dWide, LtTri* dTris, cudaStream_t stream);
 int lt_launch_inner_flags(const RefNode* dNodes, int nodeCount, int* dFlags, cudaStream_t stream);
+int lt_launch_build_threaded(const RefNode* dNodes, int nodeCount, LtThreadNode* dOut, cudaStream_t stream);
 size_t lt_scan_temp_bytes(int n);
 int lt_launch_exclusive_scan(void* dTemp, size_t tempBytes, const int* dIn, int* dOut, int n, cudaStream_t stream);
 // dWork: one zero-initialisable int of device memory (work counter of the persistent kernels)
@@ -99,6 +100,7 @@ struct lt_scene {
   LtWideNode* dWide = nullptr;
   LtTri* dTris = nullptr;
   LtThreadNode* dThread = nullptr;  // 8 octant copies in visit order, small scenes only
+  LtThreadNode* dThreadBig = nullptr;  // the same for a large scene, built on the device, for coherent-ray launches
   LtSceneDev dev = {};
 };
 

@@ -77,11 +77,12 @@ __global__ void __launch_bounds__(LT_BLOCK) k_flat(LtSceneDev sc, LtLaunch L, fl
 // same software-pipelined traversal as k_wf_trace; the lens path (basic.cu:245-298) is two more rays of the same
 // lane.  Same tests in the same order per ray as k_flat, hence the same picture (LT_FLAG_NO_STREAM selects k_flat;
 // tests compare the two).
+template <bool THREADED>
 __global__ void __launch_bounds__(LT_BLOCK) k_flat_stream(LtSceneDev sc, LtLaunch L, float* __restrict__ out,
                                                           int* __restrict__ work) {
   extern __shared__ int smemStack[];
   int* stk = smemStack + threadIdx.x;
-  int* list = smemStack + lt_stack_levels(sc) * LT_BLOCK + threadIdx.x;
+  int* list = smemStack + (THREADED ? 0 : lt_stack_levels(sc) * LT_BLOCK) + threadIdx.x;
   const unsigned stkAddr = (unsigned)__cvta_generic_to_shared(stk);
   const unsigned fifoAddr = (unsigned)__cvta_generic_to_shared(list);
   const unsigned lane = threadIdx.x & 31u;
@@ -106,8 +107,14 @@ __global__ void __launch_bounds__(LT_BLOCK) k_flat_stream(LtSceneDev sc, LtLaunc
     float r2w = 0.0f;
     int ignore = -1;
     for (int stage = 0; stage < 3; stage++) {  // 0 camera ray, 1 and 2 the rays through a lens (basic.cu:245-298)
-      trav_begin<false>(t, sc, ignore, tInit, false, cnt);
-      while (!trav_iter_lean<false>(t, sc, stkAddr, fifoAddr, epsThr, L.iterNodeSteps, L.iterTriTests, cnt)) {
+      if (THREADED) {  // stackless walk of the ray's octant copy (sc.tnodes: here the copies built for coherent rays)
+        trav_begin_threaded(t, sc, ignore, tInit, false);
+        while (!trav_iter_threaded(t, sc.tnodes, sc.tris, fifoAddr, epsThr, 2 * L.iterNodeSteps, L.iterTriTests)) {
+        }
+      } else {
+        trav_begin<false>(t, sc, ignore, tInit, false, cnt);
+        while (!trav_iter_lean<false>(t, sc, stkAddr, fifoAddr, epsThr, L.iterNodeSteps, L.iterTriTests, cnt)) {
+        }
       }
       const Hit h = t.h;
       if (stage == 0) {
@@ -321,6 +328,57 @@ __global__ void k_build_wide(const RefNode* __restrict__ nodes, int n, const int
   wide[innerRank[i]] = w;
 }
 
+// Threaded form of a LARGE tree (LtThreadNode, see lens_trace_b200_device.cuh; small trees are threaded on the host,
+// lt_capi.cu: build_threaded): one thread per reference node walks from the root to its node through the
+// depth-first index ranges (the left subtree of inner node i is [i+1, offset), the right one [offset, end)) and
+// accumulates, for all eight sign octants at once, the node's position in that octant's visit order -- descending
+// into the child the octant visits second skips the whole subtree of the one it visits first.
+__global__ void k_build_threaded(const RefNode* __restrict__ nodes, int n, LtThreadNode* __restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  int pos[8];
+#pragma unroll
+  for (int o = 0; o < 8; o++) pos[o] = 0;
+  int i = 0, end = n;
+  while (i != t) {
+    const int right = nodes[i].offset, axis = nodes[i].axis;
+    const int sizeL = right - (i + 1), sizeR = end - right;
+    const bool goRight = t >= right;
+#pragma unroll
+    for (int o = 0; o < 8; o++) {
+      const bool neg = (o >> axis) & 1;       // this octant visits the second child first (basic.cu:180-186)
+      const bool childIsFar = goRight != neg;
+      pos[o] += 1 + (childIsFar ? (neg ? sizeR : sizeL) : 0);
+    }
+    if (goRight) {
+      i = right;
+    } else {
+      end = right;
+      i = i + 1;
+    }
+  }
+  const RefNode r = nodes[t];
+  const bool leaf = r.primitiveCount > 0;
+  const int size = end - t;
+#pragma unroll
+  for (int o = 0; o < 8; o++) {
+    const int e = pos[o] + size;
+    const int skip = e >= n ? LT_DONE : o * n + e;
+    const bool nx = o & 1, ny = o & 2, nz = o & 4;
+    LtThreadNode rec;
+    rec.a = make_float4(nx ? r.boundsMax[0] : r.boundsMin[0], ny ? r.boundsMax[1] : r.boundsMin[1],
+                        nz ? r.boundsMax[2] : r.boundsMin[2], nx ? r.boundsMin[0] : r.boundsMax[0]);
+    rec.b = make_float4(ny ? r.boundsMin[1] : r.boundsMax[1], nz ? r.boundsMin[2] : r.boundsMax[2],
+                        __int_as_float(leaf ? ~r.offset : 0), __int_as_float(skip));
+    out[(size_t)o * n + pos[o]] = rec;
+  }
+}
+
+int lt_launch_build_threaded(const RefNode* dNodes, int nodeCount, LtThreadNode* dOut, cudaStream_t stream) {
+  k_build_threaded<<<(nodeCount + 127) / 128, 128, 0, stream>>>(dNodes, nodeCount, dOut);
+  return 1;
+}
+
 __global__ void k_build_tris(const RefPrim* __restrict__ prims, int n, LtTri* __restrict__ tris) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -387,15 +445,20 @@ static void opt_in_smem(size_t smem) {
   cudaFuncSetAttribute(k_path<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_MAX_TRAVERSAL_SMEM);
   cudaFuncSetAttribute(k_path<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_MAX_TRAVERSAL_SMEM);
   cudaFuncSetAttribute(k_primary_hits, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_MAX_TRAVERSAL_SMEM);
-  cudaFuncSetAttribute(k_flat_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_MAX_TRAVERSAL_SMEM);
+  cudaFuncSetAttribute(k_flat_stream<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_MAX_TRAVERSAL_SMEM);
 }
 
 static int tile_blocks(int width, int height) { return ((width + 15) / 16) * ((height + 7) / 8); }
 
 // the threaded tree is used by the exact, uncounted kernels only (the stats kernels count in the stack traversal,
 // whose tests are the same ones; LT_FLAG_NO_THREADED = 16 selects the stack traversal for comparison)
-static LtSceneDev scene_for_flags(const LtSceneDev& sc, int flags) {
+// coherent: the launch traces camera rays and shadow rays towards a light only -- a large scene's threaded copies
+// (tnodesCoherent) then pay (1 M triangles, 1080p: primary rays 0.80 instead of 1.00 ms, primary + shadow 0.97 instead
+// of 1.11 ms); for the incoherent rays of GI they lose (56.8 instead of 42.6 ms per 16-spp frame: eight copies of
+// the tree no longer fit in L2)
+static LtSceneDev scene_for_flags(const LtSceneDev& sc, int flags, bool coherent = false) {
   LtSceneDev s = sc;
+  if (coherent && s.tnodes == nullptr) s.tnodes = s.tnodesCoherent;
   if (flags & (1 | 2 | 16)) s.tnodes = nullptr;
   return s;
 }
@@ -407,15 +470,19 @@ static int env_int(const char* name, int dflt) {
 
 int lt_launch_render(const LtSceneDev& scIn, const LtLaunch& L, float* dOut, LtCounters* dCounters, int* dWork,
                      int smCount, cudaStream_t stream) {
-  const LtSceneDev sc = scene_for_flags(scIn, L.flags);
+  // camera rays and one shadow ray per hit: the deterministic kernels and the two lighting kernels
+  const bool coherentRays = L.kernel <= 4;
+  const LtSceneDev sc = scene_for_flags(scIn, L.flags, coherentRays);
   int blocks = tile_blocks(L.width, L.height);
   size_t smem = stack_bytes(sc, (L.flags & 2) != 0);
   opt_in_smem(smem);
   bool stats = (L.flags & 1) != 0;
   bool flat = (L.kernel <= 2);
   // exact, uncounted launches of the deterministic pipelines on large scenes: persistent warps fetching tiles
-  if (flat && !(L.flags & (1 | 2 | LT_LAUNCH_FLAG_NO_STREAM)) && dWork != nullptr && sc.tnodes == nullptr &&
+  if (flat && !(L.flags & (1 | 2 | LT_LAUNCH_FLAG_NO_STREAM)) && dWork != nullptr &&
       sc.nodeCount >= env_int("LT_STREAM_MIN_NODES", 100000)) {
+    const bool threaded = sc.tnodes != nullptr;
+    if (threaded) smem = (size_t)LT_MAX_BATCH * LT_BLOCK * sizeof(int);  // the leaf FIFO only
     int blocksPerSm = (int)((200 * 1024) / smem);
     if (blocksPerSm > 8) blocksPerSm = 8;  // measured 4 .. 10: no difference (the longest tile bounds the kernel)
     if (blocksPerSm < 1) blocksPerSm = 1;
@@ -423,7 +490,8 @@ int lt_launch_render(const LtSceneDev& scIn, const LtLaunch& L, float* dOut, LtC
     const int warpsNeeded = (((L.width + 7) >> 3) * ((L.height + 3) >> 2) + 3) / 4;  // blocks of 4 warps, one tile each
     if (grid > warpsNeeded) grid = warpsNeeded;
     cudaMemsetAsync(dWork, 0, sizeof(int), stream);
-    k_flat_stream<<<grid, LT_BLOCK, smem, stream>>>(sc, L, dOut, dWork);
+    if (threaded) k_flat_stream<true><<<grid, LT_BLOCK, smem, stream>>>(sc, L, dOut, dWork);
+    else k_flat_stream<false><<<grid, LT_BLOCK, smem, stream>>>(sc, L, dOut, dWork);
     return 1;
   }
   if (flat) {

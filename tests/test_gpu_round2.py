@@ -309,3 +309,38 @@ def test_sah_tree_on_the_gpu(ctx, tmp_path):
             got = ctx.render(sc, cam, capi.make_params(L.KERNEL_GI, 160, 90, max_ray_depth=4, flags=pipe))
             assert_images_match(got, want, "SAH tree GI, flags %d" % pipe, max_outliers=3)
         sc.release()
+
+
+def test_device_built_threaded_copies(root):
+    """Large trees get their eight threaded (skip-pointer) copies from a device kernel (k_build_threaded) and use them
+    for coherent-ray launches.  LT_THREADED_MAX_NODES=0 (read once per process, hence the subprocess) sends the small
+    test scenes down that path too: deterministic and lighting kernels must still equal the oracle bit for bit, and the
+    records must equal the host-built ones the small scenes normally use."""
+    import subprocess
+    import sys
+    code = r'''
+import sys
+sys.path[:0] = [%r, %r + "/oracle", %r + "/tests"]
+import numpy as np
+import lt_oracle as O, util
+from lens_trace_b200 import capi, layouts as L
+ctx = capi.Context(0)
+for name in ("cornell_box", "cornell_box_lens", "green_wall", "single"):
+    sb = util.single_triangle_scene() if name == "single" else util.scene(name)
+    sc = ctx.upload(sb)
+    for yaw in (0.0, 0.05, -2.5):
+        cam = util.default_camera(yaw, 2)
+        for kernel in (L.KERNEL_BASIC_CU, L.KERNEL_CUSTOM_BARY, L.KERNEL_ACCUMULATOR, L.KERNEL_LIGHTING25):
+            w, h = (160, 100) if kernel != L.KERNEL_LIGHTING25 else (48, 32)
+            got = ctx.render(sc, cam, capi.make_params(kernel, w, h, flags=L.FLAG_MEGAKERNEL if kernel >= 3 else 0))
+            want = O.render(kernel, sb, cam, w, h, threads=0)
+            bad = (got.view(np.uint32) != want.view(np.uint32)).any(axis=-1).sum()
+            assert bad <= (3 if kernel >= 3 else 0), (name, yaw, kernel, int(bad))
+            stack = ctx.render(sc, cam, capi.make_params(kernel, w, h, flags=L.FLAG_NO_THREADED | (L.FLAG_MEGAKERNEL if kernel >= 3 else 0)))
+            assert (got.view(np.uint32) == stack.view(np.uint32)).all(), (name, yaw, kernel)
+    sc.release()
+print("ok")
+''' % (root, root, root)
+    env = dict(os.environ, LT_THREADED_MAX_NODES="0", LT_STREAM_MIN_NODES="0")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
