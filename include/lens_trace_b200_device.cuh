@@ -109,9 +109,9 @@ struct LtSceneDev {
   int stackDepth;             // entries a traversal stack needs (tree depth), <= 64
   int nodeCount, primCount, matCount;
   const LtThreadNode* tnodes;  // 8 * nodeCount threaded records, or NULL (scene too large for the copies)
-  const LtThreadNode* tnodesCoherent;  // the same records for a large scene (built on the device), used only by
-                                       // launches whose rays are coherent (camera rays, shadow rays towards a light):
-                                       // incoherent rays would spread over eight copies that no longer fit in L2
+  const LtThreadNode* tnodesCoherent;  // the same records for a large scene (built on the device), used only by the
+                                       // lighting kernels' megakernel launches (camera rays + shadow rays towards a
+                                       // light): incoherent rays spread over eight copies that no longer fit in L2
 };
 
 

@@ -115,6 +115,8 @@ void lt_multi_destroy(lt_ctx* ctx);
 int lt_multi_accum_reset(lt_ctx* ctx);
 int lt_internal_fail(lt_ctx* ctx, int code, const std::string& msg);  // sets the context's (and the thread's) last error
 int lt_internal_ensure_out(lt_ctx* ctx, size_t floats);
+// device -> the caller's host buffer on ctx's stream, synchronous (staged through pinned memory when pageable)
+int lt_internal_download(lt_ctx* ctx, float* host_out, const float* dSrc, size_t bytes);
 // one device's share of a render call: like lt_render_device, with the row window of a tile split
 int lt_internal_render_rows(lt_ctx* ctx, lt_scene* scene, const void* camera28, const lt_render_params* params,
                             float* device_out, int fullHeight, int rowBlock, int rowStride, int rowPhase, int sync);

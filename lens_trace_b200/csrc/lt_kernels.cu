@@ -77,12 +77,11 @@ __global__ void __launch_bounds__(LT_BLOCK) k_flat(LtSceneDev sc, LtLaunch L, fl
 // same software-pipelined traversal as k_wf_trace; the lens path (basic.cu:245-298) is two more rays of the same
 // lane.  Same tests in the same order per ray as k_flat, hence the same picture (LT_FLAG_NO_STREAM selects k_flat;
 // tests compare the two).
-template <bool THREADED>
 __global__ void __launch_bounds__(LT_BLOCK) k_flat_stream(LtSceneDev sc, LtLaunch L, float* __restrict__ out,
                                                           int* __restrict__ work) {
   extern __shared__ int smemStack[];
   int* stk = smemStack + threadIdx.x;
-  int* list = smemStack + (THREADED ? 0 : lt_stack_levels(sc) * LT_BLOCK) + threadIdx.x;
+  int* list = smemStack + lt_stack_levels(sc) * LT_BLOCK + threadIdx.x;
   const unsigned stkAddr = (unsigned)__cvta_generic_to_shared(stk);
   const unsigned fifoAddr = (unsigned)__cvta_generic_to_shared(list);
   const unsigned lane = threadIdx.x & 31u;
@@ -107,14 +106,8 @@ __global__ void __launch_bounds__(LT_BLOCK) k_flat_stream(LtSceneDev sc, LtLaunc
     float r2w = 0.0f;
     int ignore = -1;
     for (int stage = 0; stage < 3; stage++) {  // 0 camera ray, 1 and 2 the rays through a lens (basic.cu:245-298)
-      if (THREADED) {  // stackless walk of the ray's octant copy (sc.tnodes: here the copies built for coherent rays)
-        trav_begin_threaded(t, sc, ignore, tInit, false);
-        while (!trav_iter_threaded(t, sc.tnodes, sc.tris, fifoAddr, epsThr, 2 * L.iterNodeSteps, L.iterTriTests)) {
-        }
-      } else {
-        trav_begin<false>(t, sc, ignore, tInit, false, cnt);
-        while (!trav_iter_lean<false>(t, sc, stkAddr, fifoAddr, epsThr, L.iterNodeSteps, L.iterTriTests, cnt)) {
-        }
+      trav_begin<false>(t, sc, ignore, tInit, false, cnt);
+      while (!trav_iter_lean<false>(t, sc, stkAddr, fifoAddr, epsThr, L.iterNodeSteps, L.iterTriTests, cnt)) {
       }
       const Hit h = t.h;
       if (stage == 0) {
@@ -445,17 +438,18 @@ static void opt_in_smem(size_t smem) {
   cudaFuncSetAttribute(k_path<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_MAX_TRAVERSAL_SMEM);
   cudaFuncSetAttribute(k_path<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_MAX_TRAVERSAL_SMEM);
   cudaFuncSetAttribute(k_primary_hits, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_MAX_TRAVERSAL_SMEM);
-  cudaFuncSetAttribute(k_flat_stream<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_MAX_TRAVERSAL_SMEM);
+  cudaFuncSetAttribute(k_flat_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_MAX_TRAVERSAL_SMEM);
 }
 
 static int tile_blocks(int width, int height) { return ((width + 15) / 16) * ((height + 7) / 8); }
 
 // the threaded tree is used by the exact, uncounted kernels only (the stats kernels count in the stack traversal,
 // whose tests are the same ones; LT_FLAG_NO_THREADED = 16 selects the stack traversal for comparison)
-// coherent: the launch traces camera rays and shadow rays towards a light only -- a large scene's threaded copies
-// (tnodesCoherent) then pay (1 M triangles, 1080p: primary rays 0.80 instead of 1.00 ms, primary + shadow 0.97 instead
-// of 1.11 ms); for the incoherent rays of GI they lose (56.8 instead of 42.6 ms per 16-spp frame: eight copies of
-// the tree no longer fit in L2)
+// coherent: the launch traces camera rays and shadow rays towards a light only (the two lighting kernels on the
+// megakernel) -- a large scene's threaded copies (tnodesCoherent) then pay: 1 M triangles, 1080p, primary + shadow
+// 0.96 instead of 1.10 ms.  For the incoherent rays of GI they lose (56.8 instead of 42.6 ms per 16-spp frame: eight
+// copies of the tree no longer fit in L2), and the tile-fetching k_flat_stream is faster on the child-pair tree
+// (0.66 against 0.72 ms: half the dependent steps per ray)
 static LtSceneDev scene_for_flags(const LtSceneDev& sc, int flags, bool coherent = false) {
   LtSceneDev s = sc;
   if (coherent && s.tnodes == nullptr) s.tnodes = s.tnodesCoherent;
@@ -470,8 +464,8 @@ static int env_int(const char* name, int dflt) {
 
 int lt_launch_render(const LtSceneDev& scIn, const LtLaunch& L, float* dOut, LtCounters* dCounters, int* dWork,
                      int smCount, cudaStream_t stream) {
-  // camera rays and one shadow ray per hit: the deterministic kernels and the two lighting kernels
-  const bool coherentRays = L.kernel <= 4;
+  // camera rays and one shadow ray per hit: the two lighting kernels
+  const bool coherentRays = L.kernel == 3 || L.kernel == 4;
   const LtSceneDev sc = scene_for_flags(scIn, L.flags, coherentRays);
   int blocks = tile_blocks(L.width, L.height);
   size_t smem = stack_bytes(sc, (L.flags & 2) != 0);
@@ -479,10 +473,8 @@ int lt_launch_render(const LtSceneDev& scIn, const LtLaunch& L, float* dOut, LtC
   bool stats = (L.flags & 1) != 0;
   bool flat = (L.kernel <= 2);
   // exact, uncounted launches of the deterministic pipelines on large scenes: persistent warps fetching tiles
-  if (flat && !(L.flags & (1 | 2 | LT_LAUNCH_FLAG_NO_STREAM)) && dWork != nullptr &&
+  if (flat && !(L.flags & (1 | 2 | LT_LAUNCH_FLAG_NO_STREAM)) && dWork != nullptr && sc.tnodes == nullptr &&
       sc.nodeCount >= env_int("LT_STREAM_MIN_NODES", 100000)) {
-    const bool threaded = sc.tnodes != nullptr;
-    if (threaded) smem = (size_t)LT_MAX_BATCH * LT_BLOCK * sizeof(int);  // the leaf FIFO only
     int blocksPerSm = (int)((200 * 1024) / smem);
     if (blocksPerSm > 8) blocksPerSm = 8;  // measured 4 .. 10: no difference (the longest tile bounds the kernel)
     if (blocksPerSm < 1) blocksPerSm = 1;
@@ -490,8 +482,7 @@ int lt_launch_render(const LtSceneDev& scIn, const LtLaunch& L, float* dOut, LtC
     const int warpsNeeded = (((L.width + 7) >> 3) * ((L.height + 3) >> 2) + 3) / 4;  // blocks of 4 warps, one tile each
     if (grid > warpsNeeded) grid = warpsNeeded;
     cudaMemsetAsync(dWork, 0, sizeof(int), stream);
-    if (threaded) k_flat_stream<true><<<grid, LT_BLOCK, smem, stream>>>(sc, L, dOut, dWork);
-    else k_flat_stream<false><<<grid, LT_BLOCK, smem, stream>>>(sc, L, dOut, dWork);
+    k_flat_stream<<<grid, LT_BLOCK, smem, stream>>>(sc, L, dOut, dWork);
     return 1;
   }
   if (flat) {

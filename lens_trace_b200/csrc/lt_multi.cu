@@ -444,7 +444,10 @@ int lt_multi_render(lt_ctx* ctx, lt_scene* scene, const void* camera28, const lt
     }
     lt_ctx* c0 = g->ctx[0];
     cudaSetDevice(c0->device);
-    if (host_out) cudaMemcpyAsync(host_out, c0->dOut, fullFloats * sizeof(float), cudaMemcpyDeviceToHost, c0->stream);
+    if (host_out) {
+      int rc = lt_internal_download(c0, host_out, c0->dOut, fullFloats * sizeof(float));
+      if (rc != LT_OK) rcs[0] = rc;
+    }
     for (int k = 0; k < G; k++) {
       cudaSetDevice(g->ctx[k]->device);
       cudaError_t e = cudaStreamSynchronize(g->ctx[k]->stream);
