@@ -30,7 +30,7 @@ struct LtCopyPool {
   const char* src = nullptr;
   size_t bytes = 0, chunk = 0;
   int chunks = 0;
-  std::atomic<int> ready{0}, next{0}, copied{0};
+  std::atomic<int> ready{0}, next{0}, copied{0}, active{0};
 
   explicit LtCopyPool(int n) {
     for (int i = 0; i < n; i++) threads.emplace_back([this]() { run(); });
@@ -61,13 +61,20 @@ struct LtCopyPool {
         wake.wait(lock, [&]() { return quit || job != seen; });
         if (quit) return;
         seen = job;
+        active++;  // under the lock: begin() never changes the job while a copier is inside copy_some()
       }
       copy_some();
+      active.fetch_sub(1, std::memory_order_release);
     }
   }
   void begin(char* d, const char* s, size_t b, size_t c, int n) {
     {
-      std::lock_guard<std::mutex> lock(m);
+      std::unique_lock<std::mutex> lock(m);
+      while (active.load(std::memory_order_acquire) != 0) {  // a straggler of the previous job is still leaving
+        lock.unlock();
+        std::this_thread::yield();
+        lock.lock();
+      }
       dst = d; src = s; bytes = b; chunk = c; chunks = n;
       ready.store(0);
       next.store(0);

@@ -110,7 +110,6 @@ struct LtGroup {
   std::vector<cudaEvent_t> rendered, summed;
   int lastSplit = -1;               // split of the accumulators the devices hold (a change resets them)
   long long lastFloats = -1;
-  float lastExchangeMs = 0.0f;
 };
 
 extern "C" int lt_ctx_device_count(const lt_ctx* ctx) {
