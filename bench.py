@@ -630,6 +630,21 @@ def main():
         dt = time.perf_counter() - t0
         if i > 0:
             e2e_times.append(dt)
+    # the same call with the buffer the reference's callers really pass: malloc'ed, pageable memory (structures.h:62,76;
+    # lt_render stages it through its own pinned buffer)
+    pageable_ms = None
+    if world == 1:
+        pageable = np.empty((h, w, 3), dtype=np.float32)
+        pageable.fill(0.0)  # touch the pages
+        pt = []
+        for i in range(max(2, min(args.steps, 3)) + 1):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            ctx.render_into(scene, cam, make_step_params(), pageable.ctypes.data)
+            torch.cuda.synchronize()
+            if i > 0:
+                pt.append((time.perf_counter() - t0) * 1e3)
+        pageable_ms = sum(pt) / len(pt)
     e2e_t = torch.tensor([sum(e2e_times) / len(e2e_times)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
@@ -776,8 +791,9 @@ def main():
             "roofline": roof,
             "e2e": {"value": rays / e2e_s / 1e6, "unit": "Mrays/s", "ms_per_step": e2e_s * 1e3,
                     "h2d_bytes_per_step": 28, "d2h_bytes_per_step": int(w * h * 3 * 4),
-                    "api": "lt_render (C-ABI, host output buffer)" if world == 1 else
-                    "lt_render_device + NCCL all-reduce + D2H on rank 0"},
+                    "api": "lt_render (C-ABI, pinned host output buffer)" if world == 1 else
+                    "lt_render_device + NCCL all-reduce + D2H on rank 0",
+                    "ms_per_step_pageable_buffer": pageable_ms},
             "gpu_launches": args.steps * launches_per_step,
             "clocks": clocks,
         }
