@@ -210,6 +210,11 @@ int lt_debug_hemisphere(lt_ctx* ctx, const float* u1, const float* u2, const flo
 int lt_debug_gather_peak(lt_ctx* ctx, uint64_t table_bytes, int dependent, int ilp, int blocks_per_sm, int iters,
                          double* out_gbs, double* out_ns_per_load);
 
+/* Host-only (no device needed): the image rows device `device` of `devices` renders in a tile split (LT_SPLIT_TILES),
+ * in the order of its local rows; returns their number (out_rows may be NULL to ask for it), negative on bad
+ * arguments.  For tests of the partition on a machine without a GPU. */
+int lt_debug_tile_rows(int height, int devices, int device, int32_t* out_rows, int capacity);
+
 /* Host-only (no device needed): the threaded form of a reference node array that lt_scene_upload builds for
  * small trees -- 8 copies of node_count 32-byte records {lo.x lo.y lo.z hi.x | hi.y hi.z link skip}, copy o in
  * the order the reference's traversal (basic.cu:156-196) visits the nodes for rays whose direction signs are

@@ -18,7 +18,7 @@ SYMBOLS = [
     "lt_api_version", "lt_ctx_create", "lt_ctx_destroy", "lt_last_error", "lt_ctx_set_stream", "lt_scene_upload",
     "lt_scene_release", "lt_render", "lt_render_device", "lt_accum_reset", "lt_accum_read", "lt_primary_hits",
     "lt_last_stats", "lt_kernel_from_path", "lt_kernel_name", "lt_debug_random", "lt_debug_hemisphere", "lt_debug_build_threaded", "lt_plugin_load", "lt_render_plugin", "lt_primary_hits_flags", "lt_scene_build_lbvh", "lt_scene_download", "lt_scene_info",
-    "lt_debug_gather_peak", "lt_ctx_create_multi", "lt_ctx_device_count", "lt_host_register", "lt_host_unregister",
+    "lt_debug_gather_peak", "lt_ctx_create_multi", "lt_ctx_device_count", "lt_host_register", "lt_host_unregister", "lt_debug_tile_rows",
 ]
 
 
@@ -61,6 +61,7 @@ def load():
     lib.lt_ctx_device_count.argtypes = [C.c_void_p]
     lib.lt_host_register.argtypes = [C.c_void_p, C.c_uint64]
     lib.lt_host_unregister.argtypes = [C.c_void_p]
+    lib.lt_debug_tile_rows.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
     lib.lt_ctx_destroy.argtypes = [C.c_void_p]
     lib.lt_ctx_destroy.restype = None
     lib.lt_last_error.argtypes = [C.c_void_p]
@@ -262,6 +263,17 @@ class Scene:
         if self.h and self.ctx.h:
             self.ctx.lib.lt_scene_release(self.ctx.h, self.h)
         self.h = None
+
+
+def tile_rows(height, devices, device):
+    """Host-only: image rows device `device` of `devices` renders in a tile split, in local-row order."""
+    lib = load()
+    n = lib.lt_debug_tile_rows(height, devices, device, None, 0)
+    if n < 0:
+        raise LtError("lt_debug_tile_rows: bad arguments")
+    out = np.zeros(n, np.int32)
+    lib.lt_debug_tile_rows(height, devices, device, out.ctypes.data, n)
+    return out
 
 
 THREAD_NODE = np.dtype([("lo", "<f4", 3), ("hix", "<f4"), ("hiy", "<f4"), ("hiz", "<f4"), ("link", "<i4"), ("skip", "<i4")])

@@ -292,6 +292,22 @@ static int tile_rows_of(int height, int G, int g) {
   return rows;
 }
 
+// Host-only (no device needed): the image rows device `device` of `devices` renders in a tile split, in the order of
+// its local rows -- the mapping the kernels apply (lt_device.cuh: lt_image_row) to the row count lt_multi_render hands
+// them.  Exposed so that the partition can be checked on a machine without a GPU.
+extern "C" int lt_debug_tile_rows(int height, int devices, int device, int32_t* out_rows, int capacity) {
+  if (height < 1 || devices < 1 || device < 0 || device >= devices) return LT_ERR_INVALID;
+  const int rows = tile_rows_of(height, devices, device);
+  if (out_rows) {
+    if (capacity < rows) return LT_ERR_INVALID;
+    for (int j = 0; j < rows; j++) {
+      const int b = j / LT_TILE_ROWS;
+      out_rows[j] = (b * devices + device) * LT_TILE_ROWS + (j - b * LT_TILE_ROWS);
+    }
+  }
+  return rows;
+}
+
 int lt_multi_render(lt_ctx* ctx, lt_scene* scene, const void* camera28, const lt_render_params* params, float* host_out) {
   LtGroup* g = ctx->group;
   if (!scene || !camera28 || !params) return lt_internal_fail(ctx, LT_ERR_INVALID, "lt_render: NULL argument");

@@ -77,3 +77,23 @@ def test_two_rank_split_equals_sequential_mean(tmp_path):
     for f in range(world * frames_per_rank):
         O.accumulate(acc, O.render(L.KERNEL_ACCUMULATOR, sb, util.default_camera(0.0, f), 40, 30), f)
     np.testing.assert_allclose(combined, acc, rtol=2e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("height", [1, 7, 8, 9, 75, 1080, 2160])
+@pytest.mark.parametrize("devices", [1, 2, 3, 4, 8, 16])
+def test_tile_split_partitions_the_image_rows(height, devices):
+    """LT_SPLIT_TILES (lt_multi.cu): blocks of 8 rows dealt round-robin -- every image row belongs to exactly one
+    device, local rows ascend, and the shares differ by at most one block."""
+    from lens_trace_b200 import capi
+    seen = []
+    sizes = []
+    for g in range(devices):
+        rows = capi.tile_rows(height, devices, g)
+        assert (np.diff(rows) > 0).all()
+        assert ((rows // 8) % devices == g).all()
+        seen += rows.tolist()
+        sizes.append(len(rows))
+    assert sorted(seen) == list(range(height))
+    assert max(sizes) - min(sizes) <= 8
+    with pytest.raises(capi.LtError):
+        capi.tile_rows(height, devices, devices)
