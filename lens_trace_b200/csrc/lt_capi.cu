@@ -793,7 +793,7 @@ int lt_internal_render_rows(lt_ctx* ctx, lt_scene* scene, const void* camera28, 
 // Result -> the caller's host buffer.  The reference hands render() a malloc'ed (pageable) pOutputBuffer
 // (src/cuda/renderer_cuda.cpp:137-139: cuMemcpyDtoH); a plain cudaMemcpy into pageable memory runs at a third of the
 // link rate because the driver stages it in small pieces.  Here: pinned or registered destinations get one DMA; a
-// pageable destination is filled through the context's own pinned staging buffer in 2 MB chunks -- the DMA of chunk
+// pageable destination is filled through the context's own pinned staging buffer in 1 MB chunks -- the DMA of chunk
 // k+1 overlaps the host-side copy of chunk k, and the host side is spread over a few threads.  (Registering the
 // caller's buffer behind its back is not an option: a cached registration outlives a free()/mmap() of the same
 // address range and would then receive the frame in pages the caller no longer sees.)
@@ -820,7 +820,15 @@ int lt_internal_download(lt_ctx* ctx, float* host_out, const float* dSrc, size_t
     CK(cudaStreamSynchronize(ctx->stream));
     return LT_OK;
   }
-  const size_t kChunk = 2u << 20, kMaxStage = 256u << 20;
+  static size_t kChunk = 0;  // staging granularity (LT_DOWNLOAD_CHUNK_KB)
+  if (kChunk == 0) {
+    const char* e = getenv("LT_DOWNLOAD_CHUNK_KB");
+    long kb = e ? atol(e) : 1024;  // measured 256 KB .. 2 MB with 8 .. 16 copier threads: 1 MB and 8 threads are best (0.68 ms per 1080p call)
+    if (kb < 64) kb = 64;
+    if (kb > 65536) kb = 65536;
+    kChunk = (size_t)kb << 10;
+  }
+  const size_t kMaxStage = 256u << 20;
   if (!ctx->copyPool) ctx->copyPool = new LtCopyPool(threadsEnv - 1);
   if (ctx->stageBytes < (bytes < kMaxStage ? bytes : kMaxStage)) {
     if (ctx->stage) cudaFreeHost(ctx->stage);
